@@ -1,0 +1,70 @@
+/*
+ * zra_b200.h — additive device-level C ABI of zra-b200.
+ *
+ * zra.h keeps the reference's host-pointer contract. The functions here take DEVICE pointers
+ * (plain void*, no torch / CUDA types in the signatures; a CUDA stream is passed as void*,
+ * NULL = the legacy default stream) so that callers who already hold archives or data in HBM —
+ * bench.py, a multi-GPU driver, a storage engine — skip the PCIe staging. Each function names
+ * the reference code path it replaces.
+ *
+ * Alignment rule for every device source pointer: the base address must be 4-byte aligned and
+ * the allocation must be readable up to the next multiple of 4 bytes past `size` (any
+ * cudaMalloc / torch allocation satisfies this).
+ */
+#ifndef ZRA_B200_DEVICE_H
+#define ZRA_B200_DEVICE_H
+
+#include "zra.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* A GPU context: one CUDA device, its scratch memory and pinned staging. Not thread-safe;
+ * use one context per host thread (the zra.h entry points keep one per thread internally).
+ * Stands where the reference creates a ZSTD_DCtx / ZSTD_CCtx (source/zra.cpp:43-44). */
+typedef struct ZraCudaContext ZraCudaContext;
+
+/* device < 0 selects the calling thread's current CUDA device. */
+ZRA_EXPORT ZraStatus ZraCudaCreateContext(ZraCudaContext** context, int device);
+ZRA_EXPORT void ZraCudaDestroyContext(ZraCudaContext* context);
+
+/* Text of the last CUDA / decoder failure seen by this context ("" if none). */
+ZRA_EXPORT const char* ZraCudaGetLastError(ZraCudaContext* context);
+
+/* Number of kernel launches issued through this context so far (bench.py's gpu_launches). */
+ZRA_EXPORT uint64_t ZraCudaGetLaunchCount(ZraCudaContext* context);
+
+/* One independently decodable zstd frame. */
+typedef struct ZraCudaFrame {
+  uint64_t srcOffset;   /* byte offset of the frame inside the source buffer */
+  uint64_t dstOffset;   /* byte offset of its output inside the destination buffer */
+  uint32_t srcSize;     /* compressed size */
+  uint32_t dstCapacity; /* room for its output */
+  uint32_t exact;       /* 1: must regenerate exactly dstCapacity bytes */
+  uint32_t reserved;
+} ZraCudaFrame;
+
+/* Decodes `count` independent zstd frames (host array `frames`) from dSrc to dDst, both on the
+ * device. The GPU form of the reference's per-frame ZSTD_decompressDCtx calls
+ * (source/zra.cpp:280,289,293). On failure *failedFrame (may be NULL) is the lowest failing index.
+ * frameSizes (host, may be NULL) receives the regenerated size of every frame. */
+ZRA_EXPORT ZraStatus ZraCudaDecodeFrames(ZraCudaContext* context, const void* dSrc, size_t srcSize, const ZraCudaFrame* frames,
+                                         uint32_t count, void* dDst, uint32_t* frameSizes, uint32_t* failedFrame, void* stream);
+
+/* zra::DecompressBuffer (source/zra.cpp:243-250) with archive and output resident in HBM.
+ * outputCapacity must be >= the header's uncompressed size. */
+ZRA_EXPORT ZraStatus ZraCudaDecompressBuffer(ZraCudaContext* context, const void* dArchive, size_t archiveSize, void* dOutput,
+                                             size_t outputCapacity, void* stream);
+
+/* Frame-range form used for sharding: decodes frames [firstFrame, firstFrame+frameCount)
+ * of the archive into dOutput, whose byte 0 corresponds to uncompressed offset firstFrame*frameSize.
+ * The multi-GPU equivalent of zra::FullDecompressor::Decompress (source/zra.cpp:428-436). */
+ZRA_EXPORT ZraStatus ZraCudaDecompressFrames(ZraCudaContext* context, const void* dArchive, size_t archiveSize,
+                                             uint64_t firstFrame, uint64_t frameCount, void* dOutput, size_t outputCapacity,
+                                             void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZRA_B200_DEVICE_H */

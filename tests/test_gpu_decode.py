@@ -1,0 +1,215 @@
+"""GPU parity tests of the decode path, all through the C-ABI of libzra_b200.so.
+
+Checker = the oracle (oracle/libzra_oracle.so), the committed golden vectors, and the unmodified
+reference where its prebuilt .so travelled with the snapshot (oracle/_ref)."""
+import numpy as np
+import pytest
+
+import refzra
+import zra_b200
+from common import golden_archive, golden_archives, golden_frame, golden_frames, parse_header, seek_table, sha
+from zra_b200 import synth
+
+pytestmark = pytest.mark.gpu
+needs_ref = pytest.mark.skipif(not refzra.have_ref(), reason="oracle/_ref not present")
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+
+    assert torch.cuda.is_available()
+    torch.cuda.set_device(0)
+    return torch
+
+
+@pytest.fixture(scope="module")
+def ctx(torch_cuda):
+    return zra_b200.CudaContext(0)
+
+
+def to_device(torch, a, slack=16):
+    t = torch.zeros(a.size + slack, dtype=torch.uint8, device="cuda")
+    if a.size:
+        t[: a.size] = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return t
+
+
+# ------------------------------------------------------------------ golden vectors
+@pytest.mark.parametrize("name", golden_archives())
+def test_golden_archives_host_api(name):
+    archive, meta = golden_archive(name)
+    out = zra_b200.DecompressBuffer(archive)
+    assert out.size == meta["bytes"] and sha(out) == meta["sha256"]
+
+
+@pytest.mark.parametrize("name", golden_archives())
+def test_golden_archives_device_api(torch_cuda, ctx, name):
+    torch = torch_cuda
+    archive, meta = golden_archive(name)
+    d_in = to_device(torch, archive)
+    d_out = torch.full((meta["bytes"] + 64,), 0xAA, dtype=torch.uint8, device="cuda")
+    ctx.decompress_buffer(d_in.data_ptr(), archive.size, d_out.data_ptr(), meta["bytes"], torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    host = d_out.cpu().numpy()
+    assert sha(host[: meta["bytes"]]) == meta["sha256"]
+    assert (host[meta["bytes"]:] == 0xAA).all()  # nothing written past the end
+
+
+def test_decodecorpus_frames(torch_cuda, ctx):
+    """All generative conformance frames in ONE batch (frames of very different shapes side by side)."""
+    torch = torch_cuda
+    blobs, frames, expect = [], [], []
+    src_off = dst_off = 0
+    for name in golden_frames():
+        z, meta = golden_frame(name)
+        pad = (-z.size) % 4
+        blobs.append(np.concatenate([z, np.zeros(pad, np.uint8)]))
+        frames.append((src_off, z.size, dst_off, meta["bytes"], 0))
+        expect.append((dst_off, meta))
+        src_off += z.size + pad
+        dst_off += meta["bytes"] + 3
+    src = np.concatenate(blobs)
+    d_in = to_device(torch, src)
+    d_out = torch.zeros(dst_off + 64, dtype=torch.uint8, device="cuda")
+    sizes = ctx.decode_frames(d_in.data_ptr(), src.size, frames, d_out.data_ptr(), want_sizes=True)
+    host = d_out.cpu().numpy()
+    bad = [m["name"] for (off, m), sz in zip(expect, sizes) if sz != m["bytes"] or sha(host[off: off + m["bytes"]]) != m["sha256"]]
+    assert not bad, bad
+
+
+def test_zstd_golden_rle_first_block(torch_cuda, ctx):
+    import os
+
+    from common import GOLDEN
+
+    torch = torch_cuda
+    z = np.fromfile(os.path.join(GOLDEN, "rle-first-block.zst"), dtype=np.uint8)
+    d_in = to_device(torch, z)
+    d_out = torch.full(((1 << 20) + 16,), 7, dtype=torch.uint8, device="cuda")
+    sizes = ctx.decode_frames(d_in.data_ptr(), z.size, [(0, z.size, 0, 1 << 20, 0)], d_out.data_ptr(), want_sizes=True)
+    assert sizes == [1 << 20]
+    assert not d_out[: 1 << 20].any().item()
+
+
+# ------------------------------------------------------------------ random access
+@pytest.mark.parametrize("name", ["text_f16384_l3", "text_f262144_l3", "text_f1000_l5", "mixed_f16384_l3"])
+def test_random_access_in_memory(name):
+    archive, meta = golden_archive(name)
+    full = refzra.oracle_decompress_buffer(archive)
+    n, fs = meta["bytes"], meta["frameSize"]
+    rng = np.random.default_rng(1)
+    cases = [(0, 1), (0, fs), (1, fs), (fs - 1, 2), (fs, fs), (n - 10, 9), (123, 0), (fs // 2, 3 * fs)]
+    cases += [(int(o), int(s)) for o, s in zip(rng.integers(0, n - 1, 25), rng.integers(0, 3 * fs, 25))]
+    for off, size in cases:
+        size = min(size, n - off - 1)
+        got = zra_b200.DecompressRA(archive, off, size)
+        assert np.array_equal(got, refzra.oracle_decompress_ra(archive, off, size)), (off, size)
+        assert np.array_equal(got, full[off: off + size])
+    with pytest.raises(zra_b200.ZraError) as e:
+        zra_b200.DecompressRA(archive, n - 10, 10)
+    assert e.value.code == zra_b200.StatusCode.OutOfBoundsAccess
+
+
+def test_streaming_decompressor_and_full_decompressor():
+    archive, meta = golden_archive("text_f16384_l3")
+    full = refzra.oracle_decompress_buffer(archive)
+    n, fs = meta["bytes"], meta["frameSize"]
+    calls = []
+
+    def reader(off, size):
+        calls.append((off, size))
+        return archive[off: off + size].tobytes()
+
+    d = zra_b200.Decompressor(reader)
+    assert d.header.uncompressedSize == n
+    rng = np.random.default_rng(2)
+    for off, size in [(0, n), (n - 10, 10), (5, 0), (fs, fs)] + [(int(o), 4096) for o in rng.integers(0, n - 4096, 20)]:
+        calls.clear()
+        got = d.Decompress(off, size)
+        assert np.array_equal(got, full[off: off + size]), (off, size)
+        assert len(calls) == 1  # exactly one read callback per request, like the reference
+        assert np.array_equal(got, refzra.oracle_decompress_ra(archive, off, size, in_memory_quirk=False))
+    with pytest.raises(zra_b200.ZraError):
+        d.Decompress(n - 5, 6)
+
+    fd = zra_b200.FullDecompressor(reader)
+    out = np.empty(3 * fs + 100, np.uint8)  # room for 3 frames per call
+    pieces = []
+    while True:
+        k = fd.Decompress(out)
+        if not k:
+            break
+        assert k <= 3 * fs
+        pieces.append(out[:k].copy())
+    assert np.array_equal(np.concatenate(pieces), full)
+    small = np.empty(fs - 1, np.uint8)
+    with pytest.raises(zra_b200.ZraError) as e:
+        zra_b200.FullDecompressor(reader).Decompress(small)
+    assert e.value.code == zra_b200.StatusCode.OutputBufferTooSmall
+
+
+# ------------------------------------------------------------------ errors
+def test_corruption_matches_oracle():
+    archive, _ = golden_archive("text_f16384_l3")
+    h = parse_header(archive)
+    rng = np.random.default_rng(3)
+    exact = 0
+    for i in range(40):
+        bad = archive.copy()
+        pos = int(rng.integers(h["size"], archive.size))
+        bad[pos] ^= 1 << int(rng.integers(0, 8))
+        try:
+            refzra.oracle_decompress_buffer(bad)
+            ora = None
+        except refzra.OracleError as e:
+            ora = (e.zra, e.zstd)
+        try:
+            zra_b200.DecompressBuffer(bad)
+            got = None
+        except zra_b200.ZraError as e:
+            got = (int(e.code), e.zstd_code)
+        assert (got is None) == (ora is None), (pos, got, ora)
+        exact += got == ora
+    assert exact >= 36
+    bad = archive.copy()
+    bad[8] ^= 1
+    with pytest.raises(zra_b200.ZraError) as e:
+        zra_b200.DecompressBuffer(bad)
+    assert e.value.code == zra_b200.StatusCode.HeaderInvalid
+    with pytest.raises(zra_b200.ZraError) as e:
+        zra_b200.DecompressBuffer(archive[:-7])  # truncated
+    assert e.value.code == zra_b200.StatusCode.ZStdError and e.value.zstd_code == 72
+
+
+# ------------------------------------------------------------------ bigger, fresh archives
+@needs_ref
+@pytest.mark.parametrize("kind,fs,lvl,ck,n", [
+    ("text", 16384, 3, True, 32 << 20),
+    ("text", 65536, 3, True, 64 << 20),
+    ("text", 65536, 1, False, 32 << 20),
+    ("text", 262144, 3, True, (32 << 20) + 12345),
+    ("mixed", 65536, 2, True, 32 << 20),
+    ("text", 1 << 20, 5, True, 16 << 20),
+    ("text", 3000, 9, True, 3 << 20),
+    ("zeros", 65536, 3, True, 16 << 20),
+])
+def test_reference_archives_roundtrip(torch_cuda, ctx, kind, fs, lvl, ck, n):
+    """encode (reference, host cores) -> decode (CUDA): size-independent round-trip property."""
+    torch = torch_cuda
+    data = (synth.mixed(n, period=fs) if kind == "mixed" else np.zeros(n, np.uint8) if kind == "zeros" else synth.text(n, seed=fs + lvl))
+    z = refzra.ref_compress_mt(data, lvl, fs, ck)
+    got = zra_b200.DecompressBuffer(z)
+    assert np.array_equal(got, data)
+    # device-resident path + frame-range form
+    d_in = to_device(torch, z)
+    d_out = torch.empty(n, dtype=torch.uint8, device="cuda")
+    ctx.decompress_buffer(d_in.data_ptr(), z.size, d_out.data_ptr(), n, torch.cuda.current_stream().cuda_stream)
+    assert torch.equal(d_out, torch.from_numpy(data).cuda())
+    frames = (n + fs - 1) // fs
+    f0, cnt = frames // 3, max(1, frames // 2)
+    cnt = min(cnt, frames - f0)
+    lo, hi = f0 * fs, min(n, (f0 + cnt) * fs)
+    d_part = torch.zeros(hi - lo, dtype=torch.uint8, device="cuda")
+    ctx.decompress_frames(d_in.data_ptr(), z.size, f0, cnt, d_part.data_ptr(), hi - lo, torch.cuda.current_stream().cuda_stream)
+    assert torch.equal(d_part, torch.from_numpy(data[lo:hi]).cuda())

@@ -1,0 +1,40 @@
+// decode_launch.h — host-visible launch interface of decode_kernels.cu (internal to the library).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace zrab {
+
+// Byte offsets of the per-batch device scratch regions, all 256-byte aligned.
+struct DecodeLayout {
+  size_t offDescs, offCtxs, offTabs, offLit, offSeqs, offSummary;
+  uint32_t litStride;  // bytes of literal scratch per frame
+  uint32_t seqStride;  // packed sequence records per frame
+};
+
+// Scratch needed to decode `nFrames` frames whose largest output is `maxDstCap` bytes.
+size_t decode_scratch_bytes(uint32_t nFrames, uint32_t maxDstCap, DecodeLayout* lay);
+
+// summary words (device, at offSummary): [0] lowest failing frame (0xFFFFFFFF = none),
+// [1] frames with blocks left to decode, [2] lowest frame with an inconsistent seek-table entry.
+void launch_summary_reset(void* scratch, const DecodeLayout& lay, cudaStream_t st);
+
+// Fills the descriptor region from a ZRA seek table that is resident on the device.
+void launch_build_descs(const void* archive, uint64_t tableOff, uint64_t headerSize, uint64_t archiveSize,
+                        uint64_t uncompressedSize, uint32_t frameSize, uint32_t firstFrame, uint32_t nFrames, uint64_t dstBase,
+                        void* scratch, const DecodeLayout& lay, cudaStream_t st);
+
+// Runs `rounds` rounds (one block of every frame per round). `first` resets the frame contexts.
+void launch_decode_rounds(const void* src, void* dst, uint32_t nFrames, uint32_t rounds, bool first, void* scratch,
+                          const DecodeLayout& lay, cudaStream_t st);
+
+// Checksums + final checks + summary. May be called again after extra rounds.
+void launch_frame_finish(const void* src, const void* dst, uint32_t nFrames, void* scratch, const DecodeLayout& lay,
+                         cudaStream_t st);
+
+uint32_t frame_status_offset();
+uint32_t frame_ctx_size();
+uint32_t frame_desc_size();
+
+}  // namespace zrab

@@ -1,0 +1,79 @@
+// gpu_context.h — the library's GPU context (internal). One per host thread / per C-ABI handle.
+//
+// Owns: the CUDA device binding, a private stream, grow-only device buffers (decode scratch,
+// staged input, staged output) and pinned host staging. zra::ZDCtx / zra::ZCCtx — opaque in the
+// reference, where they wrap ZSTD_DCtx / ZSTD_CCtx (source/zra.cpp:25-44) — wrap this class.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+
+#include "decode_launch.h"
+
+namespace zrab {
+
+struct DevBuf {
+  void* p{nullptr};
+  size_t cap{0};
+};
+
+struct HostFrame {  // same layout as ZraCudaFrame / zrab::FrameDesc
+  uint64_t srcOff, dstOff;
+  uint32_t srcLen, dstCap, exact, pad;
+};
+
+struct DecodeResult {
+  int zstd{0};                  // ZSTD_ErrorCode of the lowest failing frame, 0 = ok
+  uint32_t failedFrame{~0u};    // its index
+  bool cudaFailed{false};
+};
+
+// Parsed fixed header of a ZRA archive (source/zra.cpp:111-134 layout).
+struct ArchiveInfo {
+  uint32_t headerSize;  // fixed + meta + table
+  uint32_t tableSize, frameSize, metaSize;
+  uint64_t uncompressedSize;
+  uint64_t frames;
+};
+
+class GpuContext {
+ public:
+  explicit GpuContext(int device);
+  ~GpuContext();
+  GpuContext(const GpuContext&) = delete;
+  GpuContext& operator=(const GpuContext&) = delete;
+
+  bool ok() const { return ok_; }
+  const std::string& last_error() const { return lastError_; }
+  uint64_t launches() const { return launches_; }
+  cudaStream_t stream() const { return stream_; }
+  int device() const { return device_; }
+
+  // Records a CUDA failure (returns true if `e` is an error).
+  bool check(cudaError_t e, const char* what);
+  void fail(const std::string& msg) { lastError_ = msg; }
+
+  // Grow-only device buffers.
+  void* ensure(DevBuf& b, size_t bytes);
+  DevBuf scratch, stageIn, stageOut, misc;
+
+  // Decodes frames described either by a host array (`frames`) or, when frames == nullptr, by the
+  // seek table of a device-resident archive (`info`, firstFrame, dstBase). Synchronous.
+  DecodeResult decode(const void* dSrc, size_t srcSize, const HostFrame* frames, const ArchiveInfo* info, uint64_t firstFrame,
+                      uint64_t nFrames, uint32_t maxDstCap, void* dDst, uint32_t* frameSizes, cudaStream_t st);
+
+  void bind();  // cudaSetDevice(device_)
+
+ private:
+  int device_{0};
+  bool ok_{false};
+  cudaStream_t stream_{nullptr};
+  std::string lastError_;
+  uint64_t launches_{0};
+};
+
+// Thread-local default context used by the zra.h / zra.hpp host-pointer entry points.
+GpuContext* default_context();
+
+}  // namespace zrab

@@ -1,0 +1,115 @@
+// host_ops.cu — host-buffer operations: H2D staging, kernel launches, D2H of results.
+#include "host_ops.h"
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "zra_format.h"
+
+namespace zrab {
+
+namespace {
+  OpStatus cuda_failed() {
+    OpStatus s;
+    s.cuda = true;
+    return s;
+  }
+  OpStatus from_decode(const DecodeResult& r) {
+    OpStatus s;
+    if (r.cudaFailed) s.cuda = true;
+    else if (r.zstd) { s.zra = 1; s.zstd = r.zstd; }
+    return s;
+  }
+  OpStatus zra_error(int code, int zstd = 0) {
+    OpStatus s;
+    s.zra = code;
+    s.zstd = zstd;
+    return s;
+  }
+  size_t pad4(size_t n) { return (n + 3) & ~size_t(3); }
+}  // namespace
+
+OpStatus host_decompress_archive(GpuContext* g, const uint8_t* archive, size_t n, const ArchiveInfo& info, uint8_t* out) {
+  // geometry the frame-parallel decoder relies on (the reference's serial decoder never reads the table)
+  if (!info.tableSize) return zra_error(3);
+  if (info.frames && !info.frameSize) return zra_error(3);
+  if (info.frameSize && info.tableSize != table_entries(info.uncompressedSize, info.frameSize)) return zra_error(3);
+  if (n < info.headerSize) return zra_error(5);
+  uint64_t lastEntry = get_le(archive + 38 + info.metaSize + kEntrySize * (size_t)(info.tableSize - 1), 5);
+  if ((uint64_t)info.headerSize + lastEntry != n) return zra_error(1, 72);  // truncated or trailing bytes: srcSize_wrong
+  if (!info.frames) return OpStatus{};
+  cudaStream_t st = g->stream();
+  uint8_t* dIn = static_cast<uint8_t*>(g->ensure(g->stageIn, pad4(n) + 16));
+  uint8_t* dOut = static_cast<uint8_t*>(g->ensure(g->stageOut, info.uncompressedSize + 16));
+  if (!dIn || !dOut) return cuda_failed();
+  if (g->check(cudaMemcpyAsync(dIn, archive, n, cudaMemcpyHostToDevice, st), "archive upload")) return cuda_failed();
+  uint32_t maxCap = (uint32_t)std::min<uint64_t>(info.frameSize, info.uncompressedSize);
+  DecodeResult r = g->decode(dIn, n, nullptr, &info, 0, info.frames, maxCap, dOut, nullptr, st);
+  if (r.cudaFailed || r.zstd) return from_decode(r);
+  if (g->check(cudaMemcpyAsync(out, dOut, info.uncompressedSize, cudaMemcpyDeviceToHost, st), "output download") ||
+      g->check(cudaStreamSynchronize(st), "output download"))
+    return cuda_failed();
+  return OpStatus{};
+}
+
+OpStatus host_decode_frames(GpuContext* g, const uint8_t* src, size_t srcSize, const HostFrame* frames, size_t nFrames,
+                            uint32_t frameSize, uint64_t skip, uint64_t size, uint8_t* out) {
+  if (!nFrames) return OpStatus{};
+  cudaStream_t st = g->stream();
+  uint64_t staged = 0;
+  uint32_t maxCap = 0;
+  for (size_t i = 0; i < nFrames; i++) {
+    staged = std::max<uint64_t>(staged, frames[i].dstOff + frames[i].dstCap);
+    maxCap = std::max(maxCap, frames[i].dstCap);
+  }
+  (void)frameSize;
+  uint8_t* dIn = static_cast<uint8_t*>(g->ensure(g->stageIn, pad4(srcSize) + 16));
+  uint8_t* dOut = static_cast<uint8_t*>(g->ensure(g->stageOut, staged + 16));
+  if (!dIn || !dOut) return cuda_failed();
+  if (g->check(cudaMemcpyAsync(dIn, src, srcSize, cudaMemcpyHostToDevice, st), "frame upload")) return cuda_failed();
+  DecodeResult r = g->decode(dIn, srcSize, frames, nullptr, 0, nFrames, maxCap, dOut, nullptr, st);
+  if (r.cudaFailed || r.zstd) return from_decode(r);
+  if (skip + size > staged) return zra_error(5);
+  if (size && (g->check(cudaMemcpyAsync(out, dOut + skip, size, cudaMemcpyDeviceToHost, st), "output download") ||
+               g->check(cudaStreamSynchronize(st), "output download")))
+    return cuda_failed();
+  return OpStatus{};
+}
+
+OpStatus host_decompress_range(GpuContext* g, const uint8_t* archive, size_t n, const ArchiveInfo& info, uint64_t offset,
+                               uint64_t size, uint8_t* out) {
+  if (!info.frameSize) return zra_error(3);
+  if (!size) return OpStatus{};
+  const uint8_t* table = archive + 38 + info.metaSize;
+  uint64_t first = offset / info.frameSize, last = (offset + size - 1) / info.frameSize + 1;
+  if (last >= info.tableSize) return zra_error(5);
+  uint64_t a = get_le(table + kEntrySize * first, 5), b = get_le(table + kEntrySize * last, 5);
+  if (b < a || info.headerSize + b > n) return zra_error(1, 72);
+  std::vector<HostFrame> frames(last - first);
+  for (uint64_t f = first; f < last; f++) {
+    HostFrame& d = frames[f - first];
+    uint64_t fa = get_le(table + kEntrySize * f, 5), fb = get_le(table + kEntrySize * (f + 1), 5);
+    if (fb < fa || fb > b || fb - fa > 0xFFFFFFFFull) return zra_error(1, 72);
+    uint64_t begin = f * info.frameSize;
+    d.srcOff = fa - a;
+    d.srcLen = (uint32_t)(fb - fa);
+    d.dstOff = begin - first * info.frameSize;
+    d.dstCap = (uint32_t)std::min<uint64_t>(info.frameSize, info.uncompressedSize - begin);
+    d.exact = 1;
+    d.pad = 0;
+  }
+  return host_decode_frames(g, archive + info.headerSize + a, b - a, frames.data(), frames.size(), info.frameSize,
+                            offset - first * info.frameSize, size, out);
+}
+
+OpStatus host_compress_buffer(GpuContext*, const uint8_t*, size_t, uint8_t*, size_t, size_t*, int, uint32_t, bool, const uint8_t*,
+                              size_t) {
+  return zra_error(1, 1);
+}
+
+OpStatus host_compress_frames(GpuContext*, const uint8_t*, size_t, uint32_t, int, bool, uint8_t*, size_t, uint64_t*, size_t*) {
+  return zra_error(1, 1);
+}
+
+}  // namespace zrab

@@ -1,0 +1,107 @@
+// zra_cuda_api.cu — the additive device-pointer C ABI declared in include/zra_b200.h.
+#include <cstring>
+
+#include "../../include/zra_b200.h"
+#include "gpu_context.h"
+#include "zra_format.h"
+
+using namespace zrab;
+
+struct ZraCudaContext {
+  GpuContext gpu;
+  explicit ZraCudaContext(int device) : gpu(device) {}
+};
+
+namespace {
+  ZraStatus st(ZraStatusCode z, int zstd = 0) { return ZraStatus{z, zstd}; }
+  ZraStatus from(const DecodeResult& r) {
+    if (r.cudaFailed) return st(ZStdError, 1);
+    if (r.zstd) return st(ZStdError, r.zstd);
+    return st(Success);
+  }
+  static_assert(sizeof(ZraCudaFrame) == sizeof(HostFrame), "frame descriptor layouts must agree");
+
+  // Reads and validates the fixed header of a device-resident archive.
+  ZraStatus read_info(GpuContext& g, const void* dArchive, size_t n, ArchiveInfo* info, cudaStream_t s) {
+    if (n <= kFixedHeaderSize) return st(OutOfBoundsAccess);
+    uint8_t raw[kFixedHeaderSize];
+    if (g.check(cudaMemcpyAsync(raw, dArchive, sizeof(raw), cudaMemcpyDeviceToHost, s), "header readback") ||
+        g.check(cudaStreamSynchronize(s), "header readback"))
+      return st(ZStdError, 1);
+    FixedHeaderFields f = parse_fixed_header(raw);
+    if (f.magic != kZraMagic || f.version > kZraVersion) return st(HeaderInvalid);
+    if (f.version != 1) return st(ZraVersionLow);
+    info->headerSize = f.headerSize + 8;
+    info->tableSize = f.tableSize;
+    info->frameSize = f.frameSize;
+    info->metaSize = f.metaSize;
+    info->uncompressedSize = f.uncompressedSize;
+    info->frames = f.tableSize ? f.tableSize - 1 : 0;
+    if (n < info->headerSize) return st(OutOfBoundsAccess);
+    if (!f.tableSize || (info->frames && !f.frameSize)) return st(HeaderInvalid);
+    if (f.frameSize && f.tableSize != table_entries(f.uncompressedSize, f.frameSize)) return st(HeaderInvalid);
+    if ((uint64_t)kFixedHeaderSize + f.metaSize + kEntrySize * (uint64_t)f.tableSize != info->headerSize) return st(HeaderInvalid);
+    return st(Success);
+  }
+}  // namespace
+
+extern "C" {
+
+ZraStatus ZraCudaCreateContext(ZraCudaContext** context, int device) {
+  auto* c = new ZraCudaContext(device);
+  *context = c;  // returned even on failure so that ZraCudaGetLastError can explain it
+  return c->gpu.ok() ? st(Success) : st(ZStdError, 1);
+}
+
+void ZraCudaDestroyContext(ZraCudaContext* context) { delete context; }
+
+const char* ZraCudaGetLastError(ZraCudaContext* context) { return context->gpu.last_error().c_str(); }
+
+uint64_t ZraCudaGetLaunchCount(ZraCudaContext* context) { return context->gpu.launches(); }
+
+ZraStatus ZraCudaDecodeFrames(ZraCudaContext* context, const void* dSrc, size_t srcSize, const ZraCudaFrame* frames, uint32_t count,
+                              void* dDst, uint32_t* frameSizes, uint32_t* failedFrame, void* stream) {
+  GpuContext& g = context->gpu;
+  if (!g.ok()) return st(ZStdError, 1);
+  uint32_t maxCap = 0;
+  for (uint32_t i = 0; i < count; i++) maxCap = frames[i].dstCapacity > maxCap ? frames[i].dstCapacity : maxCap;
+  DecodeResult r = g.decode(dSrc, srcSize, reinterpret_cast<const HostFrame*>(frames), nullptr, 0, count, maxCap, dDst, frameSizes,
+                            static_cast<cudaStream_t>(stream));
+  if (failedFrame) *failedFrame = r.failedFrame;
+  return from(r);
+}
+
+ZraStatus ZraCudaDecompressFrames(ZraCudaContext* context, const void* dArchive, size_t archiveSize, uint64_t firstFrame,
+                                  uint64_t frameCount, void* dOutput, size_t outputCapacity, void* stream) {
+  GpuContext& g = context->gpu;
+  if (!g.ok()) return st(ZStdError, 1);
+  g.bind();
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  ArchiveInfo info;
+  ZraStatus hs = read_info(g, dArchive, archiveSize, &info, s);
+  if (hs.zra != Success) return hs;
+  if (firstFrame > info.frames || frameCount > info.frames - firstFrame) return st(OutOfBoundsAccess);
+  if (!frameCount) return st(Success);
+  uint64_t begin = firstFrame * info.frameSize;
+  uint64_t end = firstFrame + frameCount == info.frames ? info.uncompressedSize : (firstFrame + frameCount) * (uint64_t)info.frameSize;
+  if (outputCapacity < end - begin) return st(OutputBufferTooSmall);
+  uint32_t maxCap = (uint32_t)(info.frameSize < info.uncompressedSize ? info.frameSize : info.uncompressedSize);
+  return from(g.decode(dArchive, archiveSize, nullptr, &info, firstFrame, frameCount, maxCap, dOutput, nullptr, s));
+}
+
+ZraStatus ZraCudaDecompressBuffer(ZraCudaContext* context, const void* dArchive, size_t archiveSize, void* dOutput,
+                                  size_t outputCapacity, void* stream) {
+  GpuContext& g = context->gpu;
+  if (!g.ok()) return st(ZStdError, 1);
+  g.bind();
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  ArchiveInfo info;
+  ZraStatus hs = read_info(g, dArchive, archiveSize, &info, s);
+  if (hs.zra != Success) return hs;
+  if (outputCapacity < info.uncompressedSize) return st(OutputBufferTooSmall);
+  if (!info.frames) return st(Success);
+  uint32_t maxCap = (uint32_t)(info.frameSize < info.uncompressedSize ? info.frameSize : info.uncompressedSize);
+  return from(g.decode(dArchive, archiveSize, nullptr, &info, 0, info.frames, maxCap, dOutput, nullptr, s));
+}
+
+}  // extern "C"
