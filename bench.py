@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py — the driver's benchmark contract for zra-b200.
+
+Workload (BASELINE.json configs[1]): DecompressBuffer of a 1 GiB ZRA archive, 64 KiB frames,
+Zipf-word text, written by the UNMODIFIED reference at its default level 3 with checksums.
+A "step" is one whole-archive decompression. Numbers on the JSON line:
+  value     decompressed GB/s (10^9 bytes of ORIGINAL data per second), archive and output resident in
+            HBM, through the device-pointer C-ABI (ZraCudaDecompressBuffer); CUDA events, max over ranks
+  e2e       same metric through the reference-facing C-ABI ZraDecompressBuffer with pinned HOST buffers
+            (H2D of the archive and D2H of the output inside the timed region)
+  roofline  dominant kernel: algorithmic bytes (archive bytes read + original bytes written) of one
+            step / that kernel's CUDA-event time per step, against MEASURED_PEAKS.json's HBM copy bandwidth
+  cpu_baseline  the reference's own CPU path (oracle/_ref) on this box's host cores, same archive
+`--impl reference` times the reference CPU implementation alone (all host threads) on the same archive.
+N > 1 (torchrun): every rank decodes its own 1 GiB archive (weak scaling, no data-path collective).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+GIB = 1 << 30
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="zra_b200", choices=["zra_b200", "reference"])
+    ap.add_argument("--size-mib", type=int, default=1024, help="original bytes per archive (default: the 1 GiB of configs[1])")
+    ap.add_argument("--frame-size", type=int, default=65536)
+    ap.add_argument("--level", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------- workload
+def build_archive(size, frame_size, level, seed):
+    """Synthetic text + reference compressor (all host threads via the oracle/_ref harness). Cached in /tmp so
+    the reference arm and this arm, run back to back on one box, share the exact same archive."""
+    import refzra
+    from zra_b200 import synth
+
+    tag = f"/tmp/zra_bench_{size}_{frame_size}_{level}_{seed}"
+    if os.path.exists(tag + ".zra") and os.path.exists(tag + ".raw"):
+        return np.fromfile(tag + ".raw", dtype=np.uint8), np.fromfile(tag + ".zra", dtype=np.uint8)
+    if not refzra.have_ref():
+        raise RuntimeError("oracle/_ref/libzra_ref.so is missing: run __graft_entry__.build() where /root/reference exists")
+    data = synth.text(size, seed=seed)
+    archive = refzra.ref_compress_mt(data, level, frame_size, True)
+    try:
+        data.tofile(tag + ".raw")
+        archive.tofile(tag + ".zra")
+    except OSError:
+        pass
+    return data, archive
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.stop = [], set(), False
+        self.index = index
+        self.thread = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append((float(out[0]), float(out[1])))
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.thread.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": sorted(self.reasons)}
+        sm = sorted(s[0] for s in self.samples)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.samples[0][1], "reasons": sorted(self.reasons),
+                "samples": len(sm)}
+
+
+def measured_peak():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+# ---------------------------------------------------------------- CPU reference arm
+def cpu_reference(archive, data, threads, repeats=3):
+    """The reference's CPU decompression of the SAME archive: best of `repeats`."""
+    import ctypes as C
+
+    import refzra
+
+    L = refzra.ref()
+    out = np.zeros(data.size, np.uint8)  # pre-faulted
+    st = (C.c_int * 2)()
+    best = None
+    for _ in range(repeats):
+        t = time.perf_counter()
+        if threads == 1:
+            s = L.ZraDecompressBuffer(refzra._p(archive), archive.size, refzra._p(out))
+            assert s.zra == 0
+        else:
+            rc = L.ref_decompress_mt(refzra._p(archive), archive.size, refzra._p(out), out.size, threads, st)
+            assert rc == 0, list(st)
+        dt = time.perf_counter() - t
+        best = dt if best is None else min(best, dt)
+    assert np.array_equal(out, data)
+    return data.size / best / 1e9, best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import refzra
+
+    size = args.size_mib << 20
+    data, archive = build_archive(size, args.frame_size, args.level, seed=7)
+    threads = os.cpu_count() or 1
+    # one "step" = a bounded sample: the whole archive once on all host threads
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference(archive, data, threads, repeats=1)
+    times = []
+    for _ in range(max(1, min(args.steps, 5))):
+        times.append(cpu_reference(archive, data, threads, repeats=1)[1])
+    dt = sum(times) / len(times)
+    value = size / dt / 1e9
+    line = {
+        "impl": "reference", "metric": "decompress GB/s", "value": round(value, 4), "unit": "GB/s", "n_gpus": args.gpus,
+        "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"DecompressBuffer, {args.size_mib} MiB Zipf-text archive, {args.frame_size} B frames, level {args.level}, checksums",
+                   "archive_bytes": int(archive.size), "original_bytes": size, "host_threads": threads},
+        "cpu_baseline": {"value": round(value, 4), "unit": "GB/s", "cores": threads, "kind": "reference",
+                         "sample": f"whole {args.size_mib} MiB archive, {threads} threads each driving its own zra::Decompressor over a "
+                                   "disjoint frame range (harness-level parallelism; the reference itself is single-threaded)"},
+        "e2e": {"value": round(value, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------- GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    import zra_b200
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (zra-b200 has no CPU path)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    size = args.size_mib << 20
+    data, archive = build_archive(size, args.frame_size, args.level, seed=7 + rank)
+    ctx = zra_b200.CudaContext(local)
+    stream = torch.cuda.current_stream()
+    d_in = torch.zeros(archive.size + 64, dtype=torch.uint8, device="cuda")
+    d_in[: archive.size] = torch.from_numpy(archive).cuda()
+    d_out = torch.empty(size, dtype=torch.uint8, device="cuda")
+    d_ref = torch.from_numpy(data).cuda()
+
+    def step():
+        ctx.decompress_buffer(d_in.data_ptr(), archive.size, d_out.data_ptr(), size, stream.cuda_stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    assert torch.equal(d_out, d_ref), "decompressed bytes differ from the original"
+
+    # ---- timed region: device-resident
+    launches0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    with ClockSampler(local) as clocks:
+        e0.record(stream)
+        for _ in range(args.steps):
+            step()
+        e1.record(stream)
+        barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count() - launches0
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * size * args.steps / (ms_max / 1e3) / 1e9
+
+    # ---- per-kernel breakdown (separate pass with an event after every launch)
+    ctx.set_profiling(True)
+    for _ in range(args.steps):
+        step()
+    torch.cuda.synchronize()
+    prof = ctx.kernel_profile()
+    ctx.set_profiling(False)
+    kernels = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps} for k, v in prof.items() if v[1]}
+    total_kernel_ms = sum(k["ms_per_step"] for k in kernels.values())
+    top = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
+    peak, peak_kind = measured_peak()
+    alg_bytes = archive.size + size
+    top_ms = kernels[top]["ms_per_step"]
+    roofline = {
+        "bound": "hbm", "kernel": top, "achieved": round(alg_bytes / (top_ms / 1e3) / 1e9, 2), "peak": peak, "peak_kind": peak_kind,
+        "unit": "GB/s", "frac": round(alg_bytes / (top_ms / 1e3) / 1e9 / peak, 5), "traffic": None,
+        "algorithmic_bytes_per_step": int(alg_bytes), "kernel_ms_per_step": round(top_ms, 4),
+        "kernel_share_of_step": round(top_ms / total_kernel_ms, 4),
+        "whole_step": {"achieved": round(alg_bytes / (ms_max / args.steps / 1e3) / 1e9, 2),
+                       "frac": round(alg_bytes / (ms_max / args.steps / 1e3) / 1e9 / peak, 5)},
+        "kernels_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in kernels.items()},
+    }
+
+    # ---- end to end through the reference-facing C-ABI with pinned host buffers
+    h_in = torch.from_numpy(archive).pin_memory()
+    h_out = torch.empty(size, dtype=torch.uint8).pin_memory()
+    L = zra_b200.lib()
+    import ctypes as C
+
+    def e2e_step():
+        st = L.ZraDecompressBuffer(C.c_void_p(h_in.data_ptr()), archive.size, C.c_void_p(h_out.data_ptr()))
+        assert st.zra == 0, (st.zra, st.zstd)
+
+    for _ in range(2):
+        e2e_step()
+    assert np.array_equal(h_out.numpy(), data), "e2e output differs from the original"
+    e2e_steps = max(3, min(args.steps, 10))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * size * e2e_steps / float(t.item()) / 1e9
+
+    if rank == 0:
+        line = {
+            "metric": "decompress GB/s", "value": round(value, 3), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_max / args.steps, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"DecompressBuffer, {args.size_mib} MiB Zipf-text archive per GPU, {args.frame_size} B frames, "
+                                   f"level {args.level}, checksums, written by the reference compressor",
+                       "archive_bytes": int(archive.size), "original_bytes": size, "frames": (size + args.frame_size - 1) // args.frame_size,
+                       "l2": "inputs larger than L2 (archive + output >> 126 MB); no flush needed",
+                       "value_definition": "original (decompressed) bytes per second, all GPUs"},
+            "clocks": clocks.summary(),
+            "e2e": {"value": round(e2e_value, 3), "unit": "GB/s", "h2d_bytes_per_step": int(archive.size), "d2h_bytes_per_step": size,
+                    "api": "ZraDecompressBuffer (host pointers, pinned)", "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                threads = os.cpu_count() or 1
+                v1, t1 = cpu_reference(archive, data, 1, repeats=1)
+                vN, tN = cpu_reference(archive, data, threads, repeats=2)
+                line["cpu_baseline"] = {"value": round(vN, 4), "unit": "GB/s", "cores": threads, "kind": "reference",
+                                        "sample": f"the same {args.size_mib} MiB archive, all {threads} host threads (one zra::Decompressor each)",
+                                        "single_thread": {"value": round(v1, 4), "unit": "GB/s", "cores": 1,
+                                                          "sample": "zra::DecompressBuffer, faithful single-thread reference"}}
+            except Exception as e:  # the baseline must never take the GPU numbers down with it
+                line["cpu_baseline"] = {"value": None, "unit": "GB/s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

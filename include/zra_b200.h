@@ -35,6 +35,13 @@ ZRA_EXPORT const char* ZraCudaGetLastError(ZraCudaContext* context);
 /* Number of kernel launches issued through this context so far (bench.py's gpu_launches). */
 ZRA_EXPORT uint64_t ZraCudaGetLaunchCount(ZraCudaContext* context);
 
+/* Per-kernel timing for roofline reports: when enabled, a CUDA event is recorded after every kernel
+ * launch and the gaps are attributed per kernel. ZraCudaSetProfiling also clears the totals.
+ * ZraCudaGetKernelProfile enumerates index = 1, 2, ... until it returns 0. */
+ZRA_EXPORT void ZraCudaSetProfiling(ZraCudaContext* context, int enabled);
+ZRA_EXPORT int ZraCudaGetKernelProfile(ZraCudaContext* context, int index, const char** name, double* totalMs,
+                                       uint64_t* launches);
+
 /* One independently decodable zstd frame. */
 typedef struct ZraCudaFrame {
   uint64_t srcOffset;   /* byte offset of the frame inside the source buffer */

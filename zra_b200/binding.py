@@ -98,6 +98,8 @@ def lib():
         "ZraCudaDestroyContext": (None, [vp]),
         "ZraCudaGetLastError": (C.c_char_p, [vp]),
         "ZraCudaGetLaunchCount": (u64, [vp]),
+        "ZraCudaSetProfiling": (None, [vp, C.c_int]),
+        "ZraCudaGetKernelProfile": (C.c_int, [vp, C.c_int, P(C.c_char_p), P(C.c_double), P(u64)]),
         "ZraCudaDecodeFrames": (ZraStatus, [vp, vp, sz, P(CudaFrame), u32, vp, P(u32), P(u32), vp]),
         "ZraCudaDecompressBuffer": (ZraStatus, [vp, vp, sz, vp, sz, vp]),
         "ZraCudaDecompressFrames": (ZraStatus, [vp, vp, sz, u64, u64, vp, sz, vp]),
@@ -300,6 +302,18 @@ class CudaContext:
 
     def launch_count(self):
         return lib().ZraCudaGetLaunchCount(self._c)
+
+    def set_profiling(self, on):
+        lib().ZraCudaSetProfiling(self._c, 1 if on else 0)
+
+    def kernel_profile(self):
+        """{kernel name: (total ms, launches)} accumulated since set_profiling()."""
+        out, i = {}, 1
+        name, ms, n = C.c_char_p(), C.c_double(), C.c_uint64()
+        while lib().ZraCudaGetKernelProfile(self._c, i, C.byref(name), C.byref(ms), C.byref(n)):
+            out[name.value.decode()] = (ms.value, n.value)
+            i += 1
+        return out
 
     def _raise(self, st):
         if st.zra != 0:

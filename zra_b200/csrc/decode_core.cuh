@@ -59,11 +59,11 @@ struct FrameCtx {
   u32 pad;
 };
 
-// Table scratch of one frame.
+// Table scratch of one frame (HBM). The sequence tables use the compact 2-byte format.
 struct FrameTables {
-  SeqSym ll[512];
-  SeqSym ml[512];
-  SeqSym of[256];
+  CSym ll[512];
+  CSym ml[512];
+  CSym of[256];
   HufSym huf[4096];
 };
 
@@ -107,19 +107,19 @@ ZRA_DEV bool parse_frame_header(const u8* f, const FrameDesc& d, FrameCtx& c) {
 
 // ---------------------------------------------------------------- sequence table descriptor
 // Returns bytes consumed, or 0xFFFFFFFF on error.
-ZRA_DEV u32 setup_seq_table(SeqSym* table, u32* logOut, u32 type, u32 kind, const u8* src, u32 len, bool repeatOk) {
+ZRA_DEV u32 setup_seq_table(CSym* table, u32* logOut, u32 type, u32 kind, const u8* src, u32 len, bool repeatOk) {
   const u32 maxSym = kind == SEQ_LL ? kMaxLL : (kind == SEQ_ML ? kMaxML : kMaxOF);
   const u32 maxLog = kind == SEQ_OF ? kOFFSELog : kLLFSELog;
   if (type == 1) {  // RLE
     if (!len || src[0] > maxSym) return 0xFFFFFFFFu;
-    fse_build_rle_table(table, src[0], kind);
+    fse_build_compact_rle(table, src[0]);
     *logOut = 0;
     return 1;
   }
   if (type == 0) {  // predefined
-    if (kind == SEQ_LL) { fse_build_seq_table(table, kLLDefNorm, kMaxLL, kLLDefLog, kind); *logOut = kLLDefLog; }
-    else if (kind == SEQ_ML) { fse_build_seq_table(table, kMLDefNorm, kMaxML, kMLDefLog, kind); *logOut = kMLDefLog; }
-    else { fse_build_seq_table(table, kOFDefNorm, kDefaultMaxOF, kOFDefLog, kind); *logOut = kOFDefLog; }
+    if (kind == SEQ_LL) { fse_build_compact(table, kLLDefNorm, kMaxLL, kLLDefLog); *logOut = kLLDefLog; }
+    else if (kind == SEQ_ML) { fse_build_compact(table, kMLDefNorm, kMaxML, kMLDefLog); *logOut = kMLDefLog; }
+    else { fse_build_compact(table, kOFDefNorm, kDefaultMaxOF, kOFDefLog); *logOut = kOFDefLog; }
     return 0;
   }
   if (type == 3) return repeatOk ? 0 : 0xFFFFFFFFu;  // keep the previous block's table
@@ -127,7 +127,7 @@ ZRA_DEV u32 setup_seq_table(SeqSym* table, u32* logOut, u32 type, u32 kind, cons
   u32 ms = maxSym, log, err = 0;
   u32 h = fse_read_ncount(src, len, norm, &ms, &log, &err);
   if (!h || log > maxLog) return 0xFFFFFFFFu;
-  fse_build_seq_table(table, norm, ms, log, kind);
+  fse_build_compact(table, norm, ms, log);
   *logOut = log;
   return h;
 }
@@ -258,6 +258,11 @@ ZRA_DEV void block_setup(const u8* srcBase, const FrameDesc& d, FrameCtx& c, Fra
   c.seqLen = (u32)(iend - ip);
   c.blkType = BT_COMPRESSED;
   c.blkOut = 0;
+  if (!nbSeq) {  // literals only: nothing for the sequence stage to do
+    if (c.litSize > d.dstCap - c.blkDst) { frame_fail(c, ZE_DST_TOO_SMALL); return; }
+    c.blkOut = c.litSize;
+    c.dstPos = c.blkDst + c.litSize;
+  }
 }
 
 // ---------------------------------------------------------------- huf_stream (1 thread / stream)
@@ -288,68 +293,108 @@ ZRA_DEV u32 seq_ml(u64 s) { return (u32)(s >> 18) & 0x3FFFFu; }
 ZRA_DEV u32 seq_off(u64 s) { return (u32)(s >> 36); }
 constexpr u32 kMaxOffset = (1u << 28) - 1;
 
-ZRA_DEV void seq_decode(const u8* srcBase, const FrameDesc& d, FrameCtx& c, const FrameTables& t, u64* seqs, u32 seqCap) {
-  if (c.blkType != BT_COMPRESSED || c.status) return;
-  u32 produced = 0;  // bytes this block regenerates before its trailing literals
-  u32 litUsed = 0;
-  if (c.nbSeq) {
-    if (c.nbSeq > seqCap) { frame_fail(c, ZE_CORRUPTION); return; }
-    BackReader br;
-    if (!br.init(srcBase, d.srcOff + c.seqOff, c.seqLen)) { frame_fail(c, ZE_CORRUPTION); return; }
-    u32 sLL = br.read(c.llLog);
-    u32 sOF = br.read(c.ofLog);
-    br.refill();
-    u32 sML = br.read(c.mlLog);
-    u32 rep0 = c.rep[0], rep1 = c.rep[1], rep2 = c.rep[2];
-    const u32 room = d.dstCap - c.blkDst;
-    const u32 n = c.nbSeq;
-    u32 err = 0;
-    for (u32 i = 0; i < n; i++) {
-      SeqSym eLL = t.ll[sLL], eML = t.ml[sML], eOF = t.of[sOF];
-      u32 ofBits = seqsym_addbits(eOF), llBase = seqsym_base(eLL);
-      u32 offset;
-      br.refill();
-      if (ofBits > 1) {
-        offset = seqsym_base(eOF) + br.read(ofBits);
-        rep2 = rep1; rep1 = rep0; rep0 = offset;
-      } else {
-        u32 ll0 = (llBase == 0);
-        if (ofBits == 0) {
-          if (!ll0) offset = rep0;
-          else { offset = rep1; rep1 = rep0; rep0 = offset; }
-        } else {
-          u32 idx = seqsym_base(eOF) + ll0 + br.read(1);
-          u32 v = (idx == 3) ? rep0 - 1 : (idx == 1 ? rep1 : rep2);
-          v += !v;
-          if (idx != 1) rep2 = rep1;
-          rep1 = rep0; rep0 = offset = v;
-        }
-      }
-      br.refill();
-      u32 ml = seqsym_base(eML) + br.read(seqsym_addbits(eML));
-      u32 ll = llBase + br.read(seqsym_addbits(eLL));
-      br.refill();
-      if (i + 1 < n) {
-        sLL = seqsym_next(eLL) + br.read(seqsym_nbbits(eLL));
-        sML = seqsym_next(eML) + br.read(seqsym_nbbits(eML));
-        sOF = seqsym_next(eOF) + br.read(seqsym_nbbits(eOF));
-      }
-      // validation: everything seq_execute will trust
-      if (ll > c.litSize - litUsed) { err = ZE_CORRUPTION; break; }
-      litUsed += ll;
-      if ((u64)produced + ll + ml > room) { err = ZE_DST_TOO_SMALL; break; }
-      if (offset > c.blkDst + produced + ll || offset > kMaxOffset) { err = ZE_CORRUPTION; break; }
-      produced += ll + ml;
-      seqs[i] = seq_pack(ll, ml, offset);
+// Per-frame state of the sequence stage; lives in registers of the lane that owns the frame.
+struct SeqState {
+  BackReader br;
+  u32 sLL, sML, sOF;       // FSE states
+  u32 rep0, rep1, rep2;    // repeat-offset history
+  u32 litUsed, produced;   // literals consumed / bytes regenerated so far in this block
+  u32 i, n;                // sequence cursor / count
+  u32 llLog, ofLog, mlLog;
+  u32 litSize, room, blkDst;
+};
+
+// Starts the sequence stage of the current block of one frame. Returns 0 or a ZErr.
+ZRA_DEV u32 seq_begin(const u8* srcBase, const FrameDesc& d, const FrameCtx& c, u32 seqCap, SeqState& s) {
+  if (c.nbSeq > seqCap) return ZE_CORRUPTION;
+  if (!s.br.init(srcBase, d.srcOff + c.seqOff, c.seqLen)) return ZE_CORRUPTION;
+  s.llLog = c.llLog; s.ofLog = c.ofLog; s.mlLog = c.mlLog;
+  s.sLL = s.br.read(s.llLog);
+  s.sOF = s.br.read(s.ofLog);
+  s.br.refill();
+  s.sML = s.br.read(s.mlLog);
+  s.rep0 = c.rep[0]; s.rep1 = c.rep[1]; s.rep2 = c.rep[2];
+  s.litUsed = 0; s.produced = 0; s.i = 0; s.n = c.nbSeq;
+  s.litSize = c.litSize; s.room = d.dstCap - c.blkDst; s.blkDst = c.blkDst;
+  return ZE_OK;
+}
+
+// Decodes and validates ONE sequence. tLL/tML/tOF are the compact tables (shared memory in the
+// kernel), lutLL/lutML the packed baseline tables. Returns 0 or a ZErr; *rec receives the record.
+ZRA_DEV u32 seq_step(const CSym* tLL, const CSym* tML, const CSym* tOF, const u32* lutLL, const u32* lutML, SeqState& s, u64* rec) {
+  BackReader& br = s.br;
+  const u32 eLL = tLL[s.sLL], eML = tML[s.sML], eOF = tOF[s.sOF];
+  const u32 lutl = lutLL[csym_symbol((CSym)eLL)], lutm = lutML[csym_symbol((CSym)eML)];
+  const u32 ofBits = csym_symbol((CSym)eOF);
+  const u32 llBase = lutl & 0xFFFFFFu, llBits = lutl >> 24;
+  const u32 mlBase = lutm & 0xFFFFFFu, mlBits = lutm >> 24;
+  u32 offset;
+  br.refill();
+  if (ofBits > 1) {
+    offset = of_base(ofBits) + br.read(ofBits);
+    s.rep2 = s.rep1; s.rep1 = s.rep0; s.rep0 = offset;
+  } else {
+    u32 ll0 = (llBase == 0);
+    if (ofBits == 0) {
+      if (!ll0) offset = s.rep0;
+      else { offset = s.rep1; s.rep1 = s.rep0; s.rep0 = offset; }
+    } else {
+      u32 idx = 1 + ll0 + br.read(1);
+      u32 v = (idx == 3) ? s.rep0 - 1 : (idx == 1 ? s.rep1 : s.rep2);
+      v += !v;
+      if (idx != 1) s.rep2 = s.rep1;
+      s.rep1 = s.rep0; s.rep0 = offset = v;
     }
-    if (!err && br.remaining != 0) err = ZE_CORRUPTION;
-    if (err) { frame_fail(c, err); return; }
-    c.rep[0] = rep0; c.rep[1] = rep1; c.rep[2] = rep2;
   }
-  u32 lastLits = c.litSize - litUsed;
-  if ((u64)produced + lastLits > d.dstCap - c.blkDst) { frame_fail(c, ZE_DST_TOO_SMALL); return; }
-  c.blkOut = produced + lastLits;
-  c.dstPos = c.blkDst + c.blkOut;
+  br.refill();
+  const u32 ml = mlBase + br.read(mlBits);
+  const u32 ll = llBase + br.read(llBits);
+  br.refill();
+  if (s.i + 1 < s.n) {  // the last sequence leaves the states alone
+    u32 ns = csym_ns((CSym)eLL), nb = s.llLog - highbit32(ns);
+    s.sLL = (ns << nb) - (1u << s.llLog) + br.read(nb);
+    ns = csym_ns((CSym)eML); nb = s.mlLog - highbit32(ns);
+    s.sML = (ns << nb) - (1u << s.mlLog) + br.read(nb);
+    ns = csym_ns((CSym)eOF); nb = s.ofLog - highbit32(ns);
+    s.sOF = (ns << nb) - (1u << s.ofLog) + br.read(nb);
+  }
+  s.i++;
+  // validation: everything seq_execute will trust
+  if (ll > s.litSize - s.litUsed) return ZE_CORRUPTION;
+  s.litUsed += ll;
+  if (ll + ml > s.room - s.produced) return ZE_DST_TOO_SMALL;  // produced <= room is an invariant
+  if (offset > s.blkDst + s.produced + ll || offset > kMaxOffset) return ZE_CORRUPTION;
+  s.produced += ll + ml;
+  *rec = seq_pack(ll, ml, offset);
+  return ZE_OK;
+}
+
+// Finishes the block after its last sequence: stream exhaustion, trailing literals, write-back.
+ZRA_DEV u32 seq_end(const SeqState& s, FrameCtx& c) {
+  if (s.br.remaining != 0) return ZE_CORRUPTION;
+  u32 lastLits = s.litSize - s.litUsed;
+  if (lastLits > s.room - s.produced) return ZE_DST_TOO_SMALL;
+  c.rep[0] = s.rep0; c.rep[1] = s.rep1; c.rep[2] = s.rep2;
+  c.blkOut = s.produced + lastLits;
+  c.dstPos = s.blkDst + c.blkOut;
+  return ZE_OK;
+}
+
+// Whole stage for one frame, thread-serial (host logic tests; the kernel interleaves 32 frames).
+ZRA_DEV void seq_decode(const u8* srcBase, const FrameDesc& d, FrameCtx& c, const FrameTables& t, u64* seqs, u32 seqCap) {
+  if (c.blkType != BT_COMPRESSED || c.status || !c.nbSeq) return;
+  u32 lutLL[36], lutML[53];
+  for (u32 k = 0; k < 36; k++) lutLL[k] = ll_lut(k);
+  for (u32 k = 0; k < 53; k++) lutML[k] = ml_lut(k);
+  SeqState s;
+  u32 err = seq_begin(srcBase, d, c, seqCap, s);
+  while (!err && s.i < s.n) {
+    u64 rec;
+    err = seq_step(t.ll, t.ml, t.of, lutLL, lutML, s, &rec);
+    if (!err) seqs[s.i - 1] = rec;
+  }
+  if (!err) err = seq_end(s, c);
+  if (err) frame_fail(c, err);
 }
 
 }  // namespace zrab

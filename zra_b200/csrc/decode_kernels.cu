@@ -2,14 +2,20 @@
 //
 // Kernel inventory (one "round" = block r of every frame in the batch; see decode_core.cuh):
 //   k_build_descs   1 thread / frame   40-bit seek-table entries -> FrameDesc (ZRA geometry)
-//   k_block_setup   1 thread / frame   headers + Huffman/FSE table construction
-//   k_huf_decode    1 thread / stream  Huffman literal streams -> literal scratch
-//   k_seq_decode    1 thread / frame   FSE sequences -> packed records (+ validation)
-//   k_seq_execute   1 warp   / frame   literal/match copies into the output, raw/RLE blocks
+//   k_block_setup   1 thread / frame   headers + Huffman/FSE table construction, work lists
+//   k_huf_decode    persistent warps   4 lanes per frame (one per Huffman stream), 8 frames per warp,
+//                                      decode table staged in shared memory, lane-quads pull frames
+//                                      from a work list as they finish
+//   k_seq_decode    persistent warps   1 lane per frame, 32 frames per warp advance in lock-step,
+//                                      the three compact FSE tables of every frame in shared memory
+//                                      (2.5 KiB per frame), lanes pull frames from a work list
+//   k_seq_execute   1 warp / frame     literal/match copies into the output, raw/RLE blocks
 //   k_frame_finish  4 threads/ frame   XXH64 checksum + final size checks + error summary
 // Replaces the serial loop of ZSTD_decompressMultiFrame that zra::DecompressBuffer /
 // DecompressRA / Decompressor / FullDecompressor drive (source/zra.cpp:249,280-293,397-410,435).
 #include <cuda_runtime.h>
+
+#include <cstdlib>
 
 #include "decode_core.cuh"
 #include "decode_launch.h"
@@ -19,6 +25,13 @@ namespace zrab {
 
 constexpr u32 kFull = 0xFFFFFFFFu;
 constexpr u32 kLongCopy = 32;  // copies at least this long are done by the whole warp
+constexpr u32 kNone = 0xFFFFFFFFu;
+
+// Per-round work lists, filled by k_block_setup.
+struct RoundWork {
+  u32 hufCount, seqCount;  // entries appended this round
+  u32 hufNext, seqNext;    // consumer cursors
+};
 
 // ------------------------------------------------------------------------------------------
 // Seek table (5-byte little-endian entries, offsets relative to the end of the header) -> descs.
@@ -50,38 +63,213 @@ __global__ void k_build_descs(const u8* __restrict__ archive, u64 tableOff, u64 
 }
 
 __global__ void k_block_setup(const u8* __restrict__ src, const FrameDesc* __restrict__ descs, FrameCtx* __restrict__ ctxs,
-                              FrameTables* __restrict__ tabs, u32 nFrames, u32 firstRound) {
+                              FrameTables* __restrict__ tabs, u32 nFrames, u32 firstRound, RoundWork* __restrict__ work,
+                              u32* __restrict__ hufList, u32* __restrict__ seqList) {
   u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nFrames) return;
   FrameCtx c = ctxs[i];
   block_setup(src, descs[i], c, tabs[i], firstRound != 0);
   ctxs[i] = c;
+  if (c.blkType == BT_COMPRESSED && !c.status) {
+    if (c.litMode == LIT_HUF && c.litSize) hufList[atomicAdd(&work->hufCount, 1u)] = i;
+    if (c.nbSeq) seqList[atomicAdd(&work->seqCount, 1u)] = i;
+  }
 }
 
-__global__ void k_huf_decode(const u8* __restrict__ src, const FrameDesc* __restrict__ descs, FrameCtx* __restrict__ ctxs,
-                             const FrameTables* __restrict__ tabs, u8* __restrict__ lit, u32 litStride, u32 nFrames) {
-  u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-  u32 i = t >> 2, s = t & 3;
-  if (i >= nFrames) return;
-  const FrameCtx& c = ctxs[i];
-  if (c.status || c.blkType != BT_COMPRESSED || c.litMode != LIT_HUF || s >= c.nStreams) return;
-  u32 e = huf_stream(src, descs[i], c, tabs[i].huf, lit + (u64)i * litStride, s);
-  if (e) atomicCAS(&ctxs[i].status, 0u, e);
+// ------------------------------------------------------------------------------------------
+// Huffman literals. One warp = 8 frame slots x 4 lanes (lane & 3 = stream). Each slot keeps the
+// frame's single-symbol decode table (<= 2^11 entries x 2 B) in shared memory; a quad whose four
+// streams are done pulls the next frame from the work list.
+constexpr u32 kHufSlotEntries = 2048;
+constexpr u32 kHufWarpSmem = 8 * kHufSlotEntries * sizeof(HufSym);  // 32 KiB
+
+__global__ void __launch_bounds__(32) k_huf_decode(const u8* __restrict__ src, const FrameDesc* __restrict__ descs,
+                                                   FrameCtx* __restrict__ ctxs, const FrameTables* __restrict__ tabs,
+                                                   u8* __restrict__ lit, u32 litStride, RoundWork* __restrict__ work,
+                                                   const u32* __restrict__ hufList) {
+  extern __shared__ __align__(16) u8 smem[];
+  HufSym* slots = reinterpret_cast<HufSym*>(smem);
+  const u32 lane = threadIdx.x, quad = lane >> 2, s = lane & 3;
+  const u32 total = work->hufCount;
+  const HufSym* table = nullptr;
+  u32 frame = kNone;      // frame owned by this quad
+  bool quadIdle = true;   // quad has no frame
+  bool exhausted = false;
+  bool laneDone = true;   // this lane's stream is finished (or it has none)
+  BackReader br;
+  u32 i = 0, n = 0, log = 0;
+  u8* out = nullptr;
+  for (;;) {
+    // ---- hand frames to idle quads
+    if (__any_sync(kFull, quadIdle && !exhausted)) {
+      u32 f = kNone;
+      if (quadIdle && !exhausted && s == 0) {
+        u32 k = atomicAdd(&work->hufNext, 1u);
+        if (k < total) f = hufList[k];
+      }
+      f = __shfl_sync(kFull, f, lane & ~3u);
+      if (quadIdle && !exhausted && f == kNone) exhausted = true;
+      u32 got = __ballot_sync(kFull, f != kNone && s == 0);
+      while (got) {  // whole warp copies each new table into its slot
+        int leader = __ffs(got) - 1;
+        got &= got - 1;
+        u32 wf = __shfl_sync(kFull, f, leader);
+        u32 wlog = ctxs[wf].hufLog;
+        if (wlog <= 11) {
+          const uint4* g = reinterpret_cast<const uint4*>(tabs[wf].huf);
+          uint4* dsts = reinterpret_cast<uint4*>(slots + (leader >> 2) * kHufSlotEntries);
+          u32 vecs = (2u << wlog) >> 4;  // bytes / 16
+          if (vecs == 0) vecs = 1;
+          for (u32 k = lane; k < vecs; k += 32) dsts[k] = g[k];
+        }
+      }
+      __syncwarp();
+      if (f != kNone) {
+        frame = f;
+        quadIdle = false;
+        const FrameCtx& c = ctxs[f];
+        log = c.hufLog;
+        table = log <= 11 ? slots + quad * kHufSlotEntries : tabs[f].huf;
+        laneDone = true;
+        if (s < c.nStreams) {
+          u32 seg = c.nStreams == 4 ? (c.litSize + 3) / 4 : c.litSize;
+          n = (c.nStreams == 4 && s == 3) ? c.litSize - 3 * seg : seg;
+          out = lit + (u64)f * litStride + s * seg;
+          i = 0;
+          laneDone = false;
+          if (!br.init(src, descs[f].srcOff + c.strOff[s], c.strLen[s])) {
+            atomicCAS(&ctxs[f].status, 0u, (u32)ZE_CORRUPTION);
+            laneDone = true;
+          }
+          if (n == 0 && !laneDone) {  // an empty stream still has to be a bare end mark
+            if (br.remaining != 0) atomicCAS(&ctxs[f].status, 0u, (u32)ZE_CORRUPTION);
+            laneDone = true;
+          }
+        }
+      }
+    }
+    if (__all_sync(kFull, quadIdle)) break;
+    // ---- up to 4 symbols per lane; a full aligned group is stored as one 32-bit word
+    if (!laneDone) {
+      u32 k = 4 - ((u32)(uintptr_t)(out + i) & 3u);
+      if (k > n - i) k = n - i;
+      u32 word = 0;
+#pragma unroll
+      for (u32 j = 0; j < 4; j++) {
+        if (j < k) {
+          if ((j & 1) == 0) br.refill();
+          HufSym e = table[br.peek(log)];
+          br.skip(e >> 8);
+          word |= (u32)(e & 0xFFu) << (8 * j);
+        }
+      }
+      if (k == 4) {
+        *reinterpret_cast<u32*>(out + i) = word;
+      } else {
+        for (u32 j = 0; j < k; j++) out[i + j] = (u8)(word >> (8 * j));
+      }
+      i += k;
+      if (i >= n) {
+        laneDone = true;
+        if (br.remaining != 0) atomicCAS(&ctxs[frame].status, 0u, (u32)ZE_CORRUPTION);
+      }
+    }
+    u32 dm = __ballot_sync(kFull, laneDone);
+    if (!quadIdle && ((dm >> (lane & ~3u)) & 0xFu) == 0xFu) quadIdle = true;
+  }
 }
 
-__global__ void k_seq_decode(const u8* __restrict__ src, const FrameDesc* __restrict__ descs, FrameCtx* __restrict__ ctxs,
-                             const FrameTables* __restrict__ tabs, u64* __restrict__ seqs, u32 seqStride, u32 nFrames) {
-  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nFrames) return;
-  FrameCtx c = ctxs[i];
-  if (c.blkType != BT_COMPRESSED || c.status) return;
-  seq_decode(src, descs[i], c, tabs[i], seqs + (u64)i * seqStride, seqStride);
-  // status may have been raised concurrently by k_huf_decode when both run on separate streams;
-  // here they are ordered, so a plain write-back of the fields this stage owns is enough
-  FrameCtx* g = &ctxs[i];
-  if (c.status && !g->status) { g->status = c.status; g->flags = c.flags; g->blkType = c.blkType; }
-  g->rep[0] = c.rep[0]; g->rep[1] = c.rep[1]; g->rep[2] = c.rep[2];
-  g->blkOut = c.blkOut; g->dstPos = c.dstPos;
+// ------------------------------------------------------------------------------------------
+// FSE sequences. One warp = 32 frame slots, one lane per frame; all 32 decode one sequence per
+// iteration in lock-step from tables in shared memory. A lane that finishes its frame pulls the
+// next one from the work list, and the warp copies that frame's tables in cooperatively.
+constexpr u32 kSeqSlotEntries = 1280;  // ll 512 + ml 512 + of 256
+constexpr u32 kSeqSlots = 88;          // frames resident per CTA: 88 x 2560 B + LUTs = 225.7 KB of the SM's 227 KB
+constexpr u32 kSeqThreads = 96;        // three warps; lanes 88..95 idle
+constexpr u32 kSeqWarpSmem = kSeqSlots * kSeqSlotEntries * sizeof(CSym) + (36 + 53 + 7) * sizeof(u32);
+
+__global__ void __launch_bounds__(kSeqThreads) k_seq_decode(const u8* __restrict__ src, const FrameDesc* __restrict__ descs,
+                                                   FrameCtx* __restrict__ ctxs, const FrameTables* __restrict__ tabs,
+                                                   u64* __restrict__ seqs, u32 seqStride, RoundWork* __restrict__ work,
+                                                   const u32* __restrict__ seqList) {
+  extern __shared__ __align__(16) u8 smem[];
+  CSym* slots = reinterpret_cast<CSym*>(smem);
+  u32* lutLL = reinterpret_cast<u32*>(smem + kSeqSlots * kSeqSlotEntries * sizeof(CSym));
+  u32* lutML = lutLL + 36;
+  const u32 lane = threadIdx.x & 31, slot = threadIdx.x, slotBase = threadIdx.x & ~31u;
+  for (u32 k = threadIdx.x; k < 36; k += kSeqThreads) lutLL[k] = ll_lut(k);
+  for (u32 k = threadIdx.x; k < 53; k += kSeqThreads) lutML[k] = ml_lut(k);
+  __syncthreads();  // the only block-wide barrier: from here on the warps run independently
+  const CSym* tLL = slots + (slot < kSeqSlots ? slot : 0) * kSeqSlotEntries;
+  const CSym* tML = tLL + 512;
+  const CSym* tOF = tLL + 1024;
+  const u32 total = work->seqCount;
+  bool active = false, exhausted = slot >= kSeqSlots;
+  u32 frame = kNone;
+  SeqState st;
+  u64* out = nullptr;
+  for (;;) {
+    if (__any_sync(kFull, !active && !exhausted)) {
+      u32 f = kNone;
+      if (!active && !exhausted) {
+        u32 k = atomicAdd(&work->seqNext, 1u);
+        if (k < total) f = seqList[k];
+        else exhausted = true;
+      }
+      u32 got = __ballot_sync(kFull, f != kNone);
+      while (got) {
+        int who = __ffs(got) - 1;
+        got &= got - 1;
+        u32 wf = __shfl_sync(kFull, f, who);
+        const uint4* g = reinterpret_cast<const uint4*>(&tabs[wf]);
+        uint4* d = reinterpret_cast<uint4*>(slots + (slotBase + who) * kSeqSlotEntries);
+        for (u32 k = lane; k < kSeqSlotEntries * sizeof(CSym) / 16; k += 32) d[k] = g[k];
+      }
+      __syncwarp();
+      if (f != kNone) {
+        frame = f;
+        out = seqs + (u64)f * seqStride;
+        u32 err = seq_begin(src, descs[f], ctxs[f], seqStride, st);
+        if (err) {
+          FrameCtx* g = &ctxs[f];
+          if (!g->status) g->status = err;
+          g->blkType = BT_NONE;
+          g->flags |= FF_DONE;
+        } else {
+          active = true;
+        }
+      }
+    }
+    if (!__any_sync(kFull, active)) {
+      if (__all_sync(kFull, exhausted)) break;
+      continue;  // a lane whose frame failed to start fetches again
+    }
+#pragma unroll 1
+    for (u32 rep = 0; rep < 4; rep++) {
+      if (active) {
+        u64 rec;
+        u32 err = seq_step(tLL, tML, tOF, lutLL, lutML, st, &rec);
+        if (!err) out[st.i - 1] = rec;
+        if (err || st.i == st.n) {
+          FrameCtx* g = &ctxs[frame];
+          if (!err) {
+            FrameCtx tmp;
+            err = seq_end(st, tmp);
+            if (!err) {
+              g->rep[0] = tmp.rep[0]; g->rep[1] = tmp.rep[1]; g->rep[2] = tmp.rep[2];
+              g->blkOut = tmp.blkOut; g->dstPos = tmp.dstPos;
+            }
+          }
+          if (err) {
+            if (!g->status) g->status = err;
+            g->blkType = BT_NONE;
+            g->flags |= FF_DONE;
+          }
+          active = false;
+        }
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -94,9 +282,49 @@ __device__ __forceinline__ u32 warp_incl_scan(u32 v, u32 lane) {
   return v;
 }
 
-// Whole-warp forward copy, byte granular; no overlap between [dst,dst+n) and [src,src+n).
+// Whole-warp forward copy, byte granular; [dst,dst+n) and [src,src+n) do not overlap.
 __device__ __forceinline__ void warp_copy(u8* dst, const u8* src, u32 n, u32 lane) {
   for (u32 i = lane; i < n; i += 32) dst[i] = src[i];
+}
+
+// One lane copies n (< kLongCopy) bytes: all loads are issued before the stores so the lane pays
+// one memory round trip instead of n. `period` < n means the match overlaps its own output
+// (offset < length): the source is then the period-long pattern that precedes dst.
+template <bool kReadOnlySrc>
+__device__ __forceinline__ u8 ld_byte(const u8* p) {
+  // output bytes are re-read through L1 (coherent within the SM that wrote them, and only this
+  // warp writes this frame): consecutive bytes of a match then cost one L2 sector, not one each
+  return kReadOnlySrc ? __ldg(p) : *p;
+}
+
+template <bool kReadOnlySrc>
+__device__ __forceinline__ void lane_copy_short(u8* dst, const u8* src, u32 n, u32 period) {
+  if (period < n) {  // rare: short self-overlapping match, byte-serial pattern walk
+    u32 j = 0;
+    for (u32 i = 0; i < n; i++) {
+      dst[i] = ld_byte<kReadOnlySrc>(src + j);
+      if (++j == period) j = 0;
+    }
+    return;
+  }
+  // full groups of 8 with immediate offsets, then a predicated tail of at most 7
+  while (n >= 8) {
+    u8 b[8];
+#pragma unroll
+    for (u32 k = 0; k < 8; k++) b[k] = ld_byte<kReadOnlySrc>(src + k);
+#pragma unroll
+    for (u32 k = 0; k < 8; k++) dst[k] = b[k];
+    src += 8;
+    dst += 8;
+    n -= 8;
+  }
+  u8 t[7];
+#pragma unroll
+  for (u32 k = 0; k < 7; k++)
+    if (k < n) t[k] = ld_byte<kReadOnlySrc>(src + k);
+#pragma unroll
+  for (u32 k = 0; k < 7; k++)
+    if (k < n) dst[k] = t[k];
 }
 
 __global__ void __launch_bounds__(256) k_seq_execute(const u8* __restrict__ src, u8* dst, const FrameDesc* __restrict__ descs,
@@ -112,7 +340,7 @@ __global__ void __launch_bounds__(256) k_seq_execute(const u8* __restrict__ src,
   const u8* fsrc = src + d.srcOff;
   const u32 blkDst = c.blkDst;
   if (c.blkType == BT_RAW) {
-    warp_copy(frame + blkDst, fsrc + c.blkSrc, c.blkSize, lane);
+    for (u32 i = lane; i < c.blkSize; i += 32) frame[blkDst + i] = __ldg(fsrc + c.blkSrc + i);
     return;
   }
   if (c.blkType == BT_RLE) {
@@ -129,7 +357,7 @@ __global__ void __launch_bounds__(256) k_seq_execute(const u8* __restrict__ src,
   u32 pos = blkDst;  // frame-relative output cursor
   u32 litPos = 0;
   for (u32 base = 0; base < nbSeq; base += 32) {
-    u64 s = (base + lane < nbSeq) ? sq[base + lane] : 0ull;
+    u64 s = (base + lane < nbSeq) ? __ldg(sq + base + lane) : 0ull;
     u32 ll = seq_ll(s), ml = seq_ml(s), off = seq_off(s);
     u32 sumLL = warp_incl_scan(ll, lane);
     u32 sumOut = warp_incl_scan(ll + ml, lane);
@@ -142,11 +370,11 @@ __global__ void __launch_bounds__(256) k_seq_execute(const u8* __restrict__ src,
       longLit &= longLit - 1;
       u32 L = __shfl_sync(kFull, ll, who), from = __shfl_sync(kFull, myLit, who), to = __shfl_sync(kFull, myDst, who);
       if (rle) { for (u32 i = lane; i < L; i += 32) frame[to + i] = rleByte; }
-      else warp_copy(frame + to, litp + from, L, lane);
+      else { for (u32 i = lane; i < L; i += 32) frame[to + i] = __ldg(litp + from + i); }
     }
     if (ll < kLongCopy) {
       if (rle) { for (u32 i = 0; i < ll; i++) frame[myDst + i] = rleByte; }
-      else { for (u32 i = 0; i < ll; i++) frame[myDst + i] = litp[myLit + i]; }
+      else lane_copy_short<true>(frame + myDst, litp + myLit, ll, ll);
     }
     __syncwarp();
     // matches: multi-round resolution. Everything below the first pending match is final, so
@@ -173,7 +401,7 @@ __global__ void __launch_bounds__(256) k_seq_execute(const u8* __restrict__ src,
       } else {
         bool ready = pending && ml < kLongCopy && ((int)lane == first || msrc + ml <= hwm);
         if (ready) {
-          for (u32 i = 0; i < ml; i++) frame[mpos + i] = frame[msrc + i];
+          lane_copy_short<false>(frame + mpos, frame + msrc, ml, off);
           pending = false;
         }
       }
@@ -185,7 +413,7 @@ __global__ void __launch_bounds__(256) k_seq_execute(const u8* __restrict__ src,
   // trailing literals
   u32 rest = c.litSize - litPos;
   if (rle) { for (u32 i = lane; i < rest; i += 32) frame[pos + i] = rleByte; }
-  else warp_copy(frame + pos, litp + litPos, rest, lane);
+  else { for (u32 i = lane; i < rest; i += 32) frame[pos + i] = __ldg(litp + litPos + i); }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -246,6 +474,63 @@ __global__ void k_frame_finish(const u8* __restrict__ src, const u8* __restrict_
 // ------------------------------------------------------------------------------------------
 static inline u32 div_up(u64 a, u32 b) { return (u32)((a + b - 1) / b); }
 
+const char* kernel_name(int id) {
+  static const char* names[K_COUNT] = {"start", "k_build_descs", "k_block_setup", "k_huf_decode", "k_seq_decode", "k_seq_execute",
+                                       "k_frame_finish"};
+  return id >= 0 && id < K_COUNT ? names[id] : "?";
+}
+
+KernelTimer::~KernelTimer() {
+  for (size_t i = 0; i < poolCap_; i++) cudaEventDestroy(pool_[i]);
+  free(pool_);
+  free(marks_);
+}
+void KernelTimer::reset() {
+  for (int i = 0; i < K_COUNT; i++) { ms[i] = 0; launches[i] = 0; }
+  used_ = 0;
+}
+void KernelTimer::mark(int id, cudaStream_t st) {
+  if (used_ == cap_) {
+    size_t ncap = cap_ ? cap_ * 2 : 256;
+    marks_ = static_cast<Mark*>(realloc(marks_, ncap * sizeof(Mark)));
+    pool_ = static_cast<cudaEvent_t*>(realloc(pool_, ncap * sizeof(cudaEvent_t)));
+    for (size_t i = poolCap_; i < ncap; i++) cudaEventCreate(&pool_[i]);
+    poolCap_ = cap_ = ncap;
+  }
+  marks_[used_].id = id;
+  marks_[used_].ev = pool_[used_];
+  cudaEventRecord(pool_[used_], st);
+  used_++;
+}
+void KernelTimer::collect() {
+  for (size_t i = 1; i < used_; i++) {
+    if (marks_[i].id == K_START) continue;
+    float t = 0;
+    if (cudaEventElapsedTime(&t, marks_[i - 1].ev, marks_[i].ev) == cudaSuccess) {
+      ms[marks_[i].id] += t;
+      launches[marks_[i].id]++;
+    }
+  }
+  used_ = 0;
+}
+#define ZRA_MARK(id) do { if (timer) timer->mark(id, st); } while (0)
+
+static int sm_count() {
+  static int n = [] {
+    int dev = 0, v = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v > 0 ? v : 148;
+  }();
+  return n;
+}
+
+static void configure_kernels() {
+  // per device; cheap enough to repeat on every launch sequence
+  cudaFuncSetAttribute(k_seq_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSeqWarpSmem);
+  cudaFuncSetAttribute(k_huf_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHufWarpSmem);
+}
+
 size_t decode_scratch_bytes(u32 nFrames, u32 maxDstCap, DecodeLayout* lay) {
   u32 blk = maxDstCap < kBlockSizeMax ? maxDstCap : kBlockSizeMax;
   lay->litStride = (blk + 15u) & ~15u;
@@ -259,53 +544,77 @@ size_t decode_scratch_bytes(u32 nFrames, u32 maxDstCap, DecodeLayout* lay) {
   lay->offLit = take((size_t)lay->litStride * nFrames);
   lay->offSeqs = take(sizeof(u64) * (size_t)lay->seqStride * nFrames);
   lay->offSummary = take(64);
+  lay->offWork = take(sizeof(RoundWork));
+  lay->offHufList = take(sizeof(u32) * (size_t)nFrames);
+  lay->offSeqList = take(sizeof(u32) * (size_t)nFrames);
   return off;
 }
 
 void launch_build_descs(const void* archive, u64 tableOff, u64 headerSize, u64 archiveSize, u64 uncompressedSize, u32 frameSize,
-                        u32 firstFrame, u32 nFrames, u64 dstBase, void* scratch, const DecodeLayout& lay, cudaStream_t st) {
+                        u32 firstFrame, u32 nFrames, u64 dstBase, void* scratch, const DecodeLayout& lay, cudaStream_t st,
+                        KernelTimer* timer) {
   if (!nFrames) return;
   u8* s = static_cast<u8*>(scratch);
+  ZRA_MARK(K_START);
   k_build_descs<<<div_up(nFrames, 128), 128, 0, st>>>(static_cast<const u8*>(archive), tableOff, headerSize, archiveSize,
                                                       uncompressedSize, frameSize, firstFrame, nFrames, dstBase,
                                                       reinterpret_cast<FrameDesc*>(s + lay.offDescs),
                                                       reinterpret_cast<u32*>(s + lay.offSummary));
+  ZRA_MARK(K_BUILD_DESCS);
 }
 
 void launch_summary_reset(void* scratch, const DecodeLayout& lay, cudaStream_t st) {
-  // summary = {first failing frame, frames not finished, first bad seek-table entry, rounds}
-  static const u32 init[4] = {0xFFFFFFFFu, 0u, 0xFFFFFFFFu, 0u};
-  cudaMemcpyAsync(static_cast<u8*>(scratch) + lay.offSummary, init, sizeof(init), cudaMemcpyHostToDevice, st);
+  // summary = {first failing frame, frames not finished, first bad seek-table entry, unused}
+  cudaMemsetAsync(static_cast<u8*>(scratch) + lay.offSummary, 0xFF, 16, st);
+  cudaMemsetAsync(static_cast<u8*>(scratch) + lay.offSummary + 4, 0, 4, st);
 }
 
 void launch_decode_rounds(const void* src, void* dst, u32 nFrames, u32 rounds, bool first, void* scratch, const DecodeLayout& lay,
-                          cudaStream_t st) {
+                          cudaStream_t st, KernelTimer* timer) {
   if (!nFrames) return;
+  configure_kernels();
   u8* s = static_cast<u8*>(scratch);
   auto* descs = reinterpret_cast<FrameDesc*>(s + lay.offDescs);
   auto* ctxs = reinterpret_cast<FrameCtx*>(s + lay.offCtxs);
   auto* tabs = reinterpret_cast<FrameTables*>(s + lay.offTabs);
   u8* lit = s + lay.offLit;
   u64* seqs = reinterpret_cast<u64*>(s + lay.offSeqs);
+  auto* work = reinterpret_cast<RoundWork*>(s + lay.offWork);
+  u32* hufList = reinterpret_cast<u32*>(s + lay.offHufList);
+  u32* seqList = reinterpret_cast<u32*>(s + lay.offSeqList);
   const u8* in = static_cast<const u8*>(src);
+  const u32 sms = (u32)sm_count();
+  // persistent grids: as many warps as fit the SMs' shared memory, never more than there is work
+  const u32 hufWarps = sms * 6 < div_up(nFrames, 8) ? sms * 6 : div_up(nFrames, 8);
+  const u32 seqCtas = sms < div_up(nFrames, kSeqSlots) ? sms : div_up(nFrames, kSeqSlots);
   for (u32 r = 0; r < rounds; r++) {
-    k_block_setup<<<div_up(nFrames, 64), 64, 0, st>>>(in, descs, ctxs, tabs, nFrames, (first && r == 0) ? 1u : 0u);
-    k_huf_decode<<<div_up((u64)nFrames * 4, 128), 128, 0, st>>>(in, descs, ctxs, tabs, lit, lay.litStride, nFrames);
-    k_seq_decode<<<div_up(nFrames, 64), 64, 0, st>>>(in, descs, ctxs, tabs, seqs, lay.seqStride, nFrames);
+    cudaMemsetAsync(work, 0, sizeof(RoundWork), st);
+    ZRA_MARK(K_START);
+    k_block_setup<<<div_up(nFrames, 64), 64, 0, st>>>(in, descs, ctxs, tabs, nFrames, (first && r == 0) ? 1u : 0u, work, hufList,
+                                                      seqList);
+    ZRA_MARK(K_BLOCK_SETUP);
+    k_huf_decode<<<hufWarps, 32, kHufWarpSmem, st>>>(in, descs, ctxs, tabs, lit, lay.litStride, work, hufList);
+    ZRA_MARK(K_HUF_DECODE);
+    k_seq_decode<<<seqCtas, kSeqThreads, kSeqWarpSmem, st>>>(in, descs, ctxs, tabs, seqs, lay.seqStride, work, seqList);
+    ZRA_MARK(K_SEQ_DECODE);
     k_seq_execute<<<div_up((u64)nFrames * 32, 256), 256, 0, st>>>(in, static_cast<u8*>(dst), descs, ctxs, lit, lay.litStride, seqs,
                                                                  lay.seqStride, nFrames);
+    ZRA_MARK(K_SEQ_EXECUTE);
   }
 }
 
-void launch_frame_finish(const void* src, const void* dst, u32 nFrames, void* scratch, const DecodeLayout& lay, cudaStream_t st) {
+void launch_frame_finish(const void* src, const void* dst, u32 nFrames, void* scratch, const DecodeLayout& lay, cudaStream_t st,
+                         KernelTimer* timer) {
   if (!nFrames) return;
   u8* s = static_cast<u8*>(scratch);
   // "not finished" is recounted by every finish pass
   cudaMemsetAsync(s + lay.offSummary + 4, 0, 4, st);
+  ZRA_MARK(K_START);
   k_frame_finish<<<div_up((u64)nFrames * 4, 128), 128, 0, st>>>(static_cast<const u8*>(src), static_cast<const u8*>(dst),
                                                                 reinterpret_cast<const FrameDesc*>(s + lay.offDescs),
                                                                 reinterpret_cast<FrameCtx*>(s + lay.offCtxs), nFrames,
                                                                 reinterpret_cast<u32*>(s + lay.offSummary));
+  ZRA_MARK(K_FRAME_FINISH);
 }
 
 u32 frame_status_offset() { return (u32)offsetof(FrameCtx, status); }

@@ -122,6 +122,42 @@ ZRA_DEV void fse_build_seq_table(SeqSym* table, const int16_t* norm, u32 maxSymb
 
 ZRA_DEV void fse_build_rle_table(SeqSym* table, u32 s, u32 kind) { table[0] = seqsym_pack(0, seq_addbits(kind, s), 0, seq_base(kind, s)); }
 
+// ---- compact sequence tables (the format the decode kernels keep in shared memory) ----------
+// 2-byte entry: symbol (6 bits) | ns << 6, where ns is the "next state" counter of the cell
+// (range [count, 2*count) <= 1023). nbBits and the next-state base are recomputed on the fly:
+//   nbBits = log - highbit(ns),  nextStateBase = (ns << nbBits) - (1 << log)
+// Halving the entry (the reference's ZSTD_seqSymbol is 8 bytes, zstd_decompress_internal.h:62-82)
+// doubles the number of frames whose three tables fit in one SM's shared memory.
+typedef u16 CSym;
+ZRA_DEV u32 csym_symbol(CSym e) { return e & 63u; }
+ZRA_DEV u32 csym_ns(CSym e) { return (u32)e >> 6; }
+
+ZRA_DEV void fse_build_compact(CSym* table, const int16_t* norm, u32 maxSymbol, u32 log) {
+  u32 size = 1u << log, mask = size - 1, high = size - 1;
+  u16 nextv[64];
+  for (u32 s = 0; s <= maxSymbol; s++) {
+    if (norm[s] == -1) { table[high--] = (CSym)s; nextv[s] = 1; }
+    else nextv[s] = (u16)norm[s];
+  }
+  u32 step = (size >> 1) + (size >> 3) + 3, pos = 0;
+  for (u32 s = 0; s <= maxSymbol; s++) {
+    for (i32 i = 0; i < norm[s]; i++) {
+      table[pos] = (CSym)s;
+      do { pos = (pos + step) & mask; } while (pos > high);
+    }
+  }
+  for (u32 u = 0; u < size; u++) {
+    u32 s = table[u];
+    u32 ns = nextv[s]++;
+    table[u] = (CSym)(s | (ns << 6));
+  }
+}
+ZRA_DEV void fse_build_compact_rle(CSym* table, u32 s) { table[0] = (CSym)(s | (1u << 6)); }
+
+// Packed per-code lookup: baseline (24 bits) | extra bits << 24.
+ZRA_DEV u32 ll_lut(u32 code) { return kLLBase[code] | ((u32)kLLBits[code] << 24); }
+ZRA_DEV u32 ml_lut(u32 code) { return kMLBase[code] | ((u32)kMLBits[code] << 24); }
+
 // Huffman decode-table entry: symbol | nbBits << 8.
 typedef u16 HufSym;
 

@@ -1,4 +1,4 @@
-// gpu_context.cu — GPU context: device binding, buffers, and the batched decode driver.
+// gpu_context.cu — GPU context: device binding, buffers, and the chunked multi-stream decode driver.
 #include "gpu_context.h"
 
 #include <algorithm>
@@ -24,6 +24,10 @@ GpuContext::GpuContext(int device) {
   device_ = device;
   if (check(cudaSetDevice(device_), "cudaSetDevice")) return;
   if (check(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), "cudaStreamCreate")) return;
+  for (auto& s : pool_)
+    if (check(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate")) return;
+  if (check(cudaEventCreateWithFlags(&forkEvent_, cudaEventDisableTiming), "cudaEventCreate")) return;
+  if (check(cudaMallocHost(&summaryHost_, sizeof(uint32_t) * 4 * kMaxChunks), "cudaMallocHost")) return;
   ok_ = true;
 }
 
@@ -32,6 +36,10 @@ GpuContext::~GpuContext() {
   cudaSetDevice(device_);
   for (DevBuf* b : {&scratch, &stageIn, &stageOut, &misc})
     if (b->p) cudaFree(b->p);
+  for (auto& s : pool_)
+    if (s) cudaStreamDestroy(s);
+  if (forkEvent_) cudaEventDestroy(forkEvent_);
+  if (summaryHost_) cudaFreeHost(summaryHost_);
   if (stream_) cudaStreamDestroy(stream_);
 }
 
@@ -68,75 +76,160 @@ void* GpuContext::ensure(DevBuf& b, size_t bytes) {
 static size_t scratch_budget() {
   static size_t v = [] {
     const char* s = getenv("ZRA_B200_SCRATCH_MB");
-    size_t mb = s ? strtoull(s, nullptr, 10) : 6144;
+    size_t mb = s ? strtoull(s, nullptr, 10) : 8192;
     return std::max<size_t>(mb, 64) << 20;
   }();
   return v;
 }
 
+static uint32_t chunk_target() {
+  static uint32_t v = [] {
+    const char* s = getenv("ZRA_B200_CHUNKS");
+    uint32_t n = s ? (uint32_t)strtoul(s, nullptr, 10) : 4;
+    return std::max<uint32_t>(1, std::min<uint32_t>(n, 256));
+  }();
+  return v;
+}
+
+namespace {
+  struct Chunk {
+    uint64_t f0;
+    uint32_t n;
+    DecodeLayout lay;
+    uint8_t* scratch;
+    cudaStream_t st;
+    uint32_t* summary;  // pinned host words
+  };
+}  // namespace
+
 DecodeResult GpuContext::decode(const void* dSrc, size_t srcSize, const HostFrame* frames, const ArchiveInfo* info,
                                 uint64_t firstFrame, uint64_t nFrames, uint32_t maxDstCap, void* dDst, uint32_t* frameSizes,
-                                cudaStream_t st) {
+                                cudaStream_t st, const HostStaging* io) {
   DecodeResult res;
-  (void)srcSize;
   if (!nFrames) return res;
   bind();
-  // batch size: as many frames as the scratch budget allows
   DecodeLayout one;
-  size_t perFrame = decode_scratch_bytes(1, maxDstCap, &one);
-  uint64_t batch = std::max<uint64_t>(1, scratch_budget() / perFrame);
-  batch = std::min<uint64_t>(batch, nFrames);
-  batch = std::min<uint64_t>(batch, 1u << 22);
+  const size_t perFrame = decode_scratch_bytes(1, maxDstCap, &one);
+  // frames per group = what the scratch budget holds; a group is cut into chunks that run concurrently
+  const uint64_t groupFrames = std::min<uint64_t>(std::max<uint64_t>(1, scratch_budget() / perFrame), 1u << 22);
   const uint32_t baseRounds = std::max<uint32_t>(1, (maxDstCap + (1u << 17) - 1) >> 17);
+  const bool single = profiling_;  // per-kernel event timing needs one chunk on one stream
+  KernelTimer* tm = profiling_ ? &timer : nullptr;
   std::vector<uint8_t> ctxHost;
+  std::vector<Chunk> chunks;
+  auto fail_cuda = [&]() { res.cudaFailed = true; return res; };
 
-  for (uint64_t f0 = 0; f0 < nFrames; f0 += batch) {
-    uint32_t n = (uint32_t)std::min<uint64_t>(batch, nFrames - f0);
-    DecodeLayout lay;
-    size_t bytes = decode_scratch_bytes(n, maxDstCap, &lay);
-    uint8_t* s = static_cast<uint8_t*>(ensure(scratch, bytes));
-    if (!s) { res.cudaFailed = true; return res; }
-    launch_summary_reset(s, lay, st);
-    uint64_t dstBase = 0;
-    if (frames) {
-      if (check(cudaMemcpyAsync(s + lay.offDescs, frames + f0, sizeof(HostFrame) * (size_t)n, cudaMemcpyHostToDevice, st),
-                "descriptor upload")) { res.cudaFailed = true; return res; }
-    } else {
-      dstBase = firstFrame * info->frameSize;
-      launch_build_descs(dSrc, 38ull + info->metaSize, info->headerSize, srcSize, info->uncompressedSize, info->frameSize,
-                         (uint32_t)(firstFrame + f0), n, dstBase, s, lay, st);
+  for (uint64_t g0 = 0; g0 < nFrames; g0 += groupFrames) {
+    const uint64_t gN = std::min<uint64_t>(groupFrames, nFrames - g0);
+    // ---- plan the chunks of this group
+    uint32_t nChunks = single ? 1u : (uint32_t)std::min<uint64_t>(chunk_target(), std::max<uint64_t>(1, gN / 64));
+    nChunks = std::min<uint32_t>(nChunks, kMaxChunks);
+    const uint64_t per = (gN + nChunks - 1) / nChunks;
+    chunks.clear();
+    size_t total = 0;
+    for (uint64_t c0 = 0; c0 < gN; c0 += per) {
+      Chunk c;
+      c.f0 = g0 + c0;
+      c.n = (uint32_t)std::min<uint64_t>(per, gN - c0);
+      total += decode_scratch_bytes(c.n, maxDstCap, &c.lay);
+      chunks.push_back(c);
+    }
+    uint8_t* base = static_cast<uint8_t*>(ensure(scratch, total));
+    if (!base) return fail_cuda();
+    size_t off = 0;
+    for (size_t i = 0; i < chunks.size(); i++) {
+      DecodeLayout tmp;
+      chunks[i].scratch = base + off;
+      off += decode_scratch_bytes(chunks[i].n, maxDstCap, &tmp);
+      chunks[i].st = single ? st : pool_[i % kPoolStreams];
+      chunks[i].summary = summaryHost_ + 4 * i;
+    }
+    // ---- fork: the pool streams start after whatever the caller queued on `st`
+    if (!single) {
+      if (check(cudaEventRecord(forkEvent_, st), "fork event")) return fail_cuda();
+      for (int i = 0; i < kPoolStreams && i < (int)chunks.size(); i++)
+        if (check(cudaStreamWaitEvent(pool_[i], forkEvent_, 0), "fork wait")) return fail_cuda();
+    }
+    // ---- enqueue every chunk: [H2D] -> descriptors -> rounds -> finish -> summary [-> D2H]
+    auto enqueue_tail = [&](Chunk& c) -> bool {
+      launch_frame_finish(dSrc, dDst, c.n, c.scratch, c.lay, c.st, tm);
       launches_ += 1;
+      if (check(cudaMemcpyAsync(c.summary, c.scratch + c.lay.offSummary, 16, cudaMemcpyDeviceToHost, c.st), "summary readback"))
+        return false;
+      return true;
+    };
+    // output download of one chunk (second pass: with pageable host memory cudaMemcpyAsync blocks the
+    // host until the chunk is done, which must not delay the enqueueing of the other chunks)
+    auto enqueue_download = [&](Chunk& c) -> bool {
+      if (!(io && io->hostDst && frames)) return true;
+      const HostFrame& a = frames[c.f0];
+      const HostFrame& b = frames[c.f0 + c.n - 1];
+      uint64_t lo = std::max<uint64_t>(a.dstOff, io->dstSkip);
+      uint64_t hi = std::min<uint64_t>(b.dstOff + b.dstCap, io->dstSize == ~0ull ? ~0ull : io->dstSkip + io->dstSize);
+      return !(hi > lo && check(cudaMemcpyAsync(io->hostDst + (lo - io->dstSkip), static_cast<const uint8_t*>(dDst) + lo, hi - lo,
+                                                cudaMemcpyDeviceToHost, c.st), "output download"));
+    };
+    for (Chunk& c : chunks) {
+      launch_summary_reset(c.scratch, c.lay, c.st);
+      if (frames) {
+        if (io && io->hostSrc) {
+          const HostFrame& a = frames[c.f0];
+          const HostFrame& b = frames[c.f0 + c.n - 1];
+          uint64_t lo = a.srcOff, hi = b.srcOff + b.srcLen;
+          if (hi > lo && check(cudaMemcpyAsync(const_cast<uint8_t*>(static_cast<const uint8_t*>(dSrc)) + lo, io->hostSrc + lo, hi - lo,
+                                               cudaMemcpyHostToDevice, c.st), "source upload"))
+            return fail_cuda();
+        }
+        if (check(cudaMemcpyAsync(c.scratch + c.lay.offDescs, frames + c.f0, sizeof(HostFrame) * (size_t)c.n, cudaMemcpyHostToDevice,
+                                  c.st), "descriptor upload"))
+          return fail_cuda();
+      } else {
+        launch_build_descs(dSrc, 38ull + info->metaSize, info->headerSize, srcSize, info->uncompressedSize, info->frameSize,
+                           (uint32_t)(firstFrame + c.f0), c.n, firstFrame * info->frameSize, c.scratch, c.lay, c.st, tm);
+        launches_ += 1;
+      }
+      launch_decode_rounds(dSrc, dDst, c.n, baseRounds, true, c.scratch, c.lay, c.st, tm);
+      launches_ += 4ull * baseRounds;
+      if (!enqueue_tail(c)) return fail_cuda();
     }
-    uint32_t rounds = baseRounds;
-    bool first = true;
-    uint32_t summary[4];
-    for (int pass = 0;; pass++) {
-      launch_decode_rounds(dSrc, dDst, n, rounds, first, s, lay, st);
-      launch_frame_finish(dSrc, dDst, n, s, lay, st);
-      launches_ += 4ull * rounds + 1;
-      first = false;
-      if (check(cudaMemcpyAsync(summary, s + lay.offSummary, sizeof(summary), cudaMemcpyDeviceToHost, st), "summary readback") ||
-          check(cudaStreamSynchronize(st), "decode kernels")) { res.cudaFailed = true; return res; }
-      if (summary[0] != 0xFFFFFFFFu || summary[1] == 0) break;
-      // frames with more blocks than the zstd encoder would emit: keep going
-      rounds = std::min<uint32_t>(rounds * 2, 64);
-      if (pass > 1 << 16) break;
-    }
-    if (summary[0] != 0xFFFFFFFFu) {
-      uint32_t code = 0;
-      size_t off = lay.offCtxs + (size_t)summary[0] * frame_ctx_size() + frame_status_offset();
-      if (check(cudaMemcpy(&code, s + off, 4, cudaMemcpyDeviceToHost), "status readback")) { res.cudaFailed = true; return res; }
-      res.zstd = (int)code;
-      res.failedFrame = (uint32_t)(f0 + summary[0]);
-      return res;
-    }
-    if (frameSizes) {
-      ctxHost.resize((size_t)n * frame_ctx_size());
-      if (check(cudaMemcpy(ctxHost.data(), s + lay.offCtxs, ctxHost.size(), cudaMemcpyDeviceToHost), "ctx readback")) { res.cudaFailed = true; return res; }
-      for (uint32_t i = 0; i < n; i++) {
-        uint32_t v;
-        memcpy(&v, ctxHost.data() + (size_t)i * frame_ctx_size() + 12, 4);  // FrameCtx::dstPos
-        frameSizes[f0 + i] = v;
+    for (Chunk& c : chunks)
+      if (!enqueue_download(c)) return fail_cuda();
+    // ---- join, then look at every chunk's summary (in frame order, so the lowest failing frame wins)
+    for (Chunk& c : chunks) {
+      if (check(cudaStreamSynchronize(c.st), "decode kernels")) return fail_cuda();
+      if (tm) tm->collect();
+      uint32_t rounds = baseRounds;
+      bool extra = false;
+      for (int pass = 0; c.summary[0] == 0xFFFFFFFFu && c.summary[1] != 0 && pass < (1 << 16); pass++) {
+        // frames with more blocks than the zstd encoder would emit: keep going (rare, serial)
+        rounds = std::min<uint32_t>(rounds * 2, 64);
+        launch_decode_rounds(dSrc, dDst, c.n, rounds, false, c.scratch, c.lay, c.st, tm);
+        launches_ += 4ull * rounds;
+        if (!enqueue_tail(c) || check(cudaStreamSynchronize(c.st), "decode kernels")) return fail_cuda();
+        if (tm) tm->collect();
+        extra = true;
+      }
+      if (extra && c.summary[0] == 0xFFFFFFFFu &&
+          (!enqueue_download(c) || check(cudaStreamSynchronize(c.st), "output download")))
+        return fail_cuda();
+      if (c.summary[0] != 0xFFFFFFFFu) {
+        uint32_t code = 0;
+        size_t o = c.lay.offCtxs + (size_t)c.summary[0] * frame_ctx_size() + frame_status_offset();
+        if (check(cudaMemcpy(&code, c.scratch + o, 4, cudaMemcpyDeviceToHost), "status readback")) return fail_cuda();
+        for (Chunk& rest : chunks) cudaStreamSynchronize(rest.st);
+        res.zstd = (int)code;
+        res.failedFrame = (uint32_t)(c.f0 + c.summary[0]);
+        return res;
+      }
+      if (frameSizes) {
+        ctxHost.resize((size_t)c.n * frame_ctx_size());
+        if (check(cudaMemcpy(ctxHost.data(), c.scratch + c.lay.offCtxs, ctxHost.size(), cudaMemcpyDeviceToHost), "ctx readback"))
+          return fail_cuda();
+        for (uint32_t i = 0; i < c.n; i++) {
+          uint32_t v;
+          memcpy(&v, ctxHost.data() + (size_t)i * frame_ctx_size() + 12, 4);  // FrameCtx::dstPos
+          frameSizes[c.f0 + i] = v;
+        }
       }
     }
   }

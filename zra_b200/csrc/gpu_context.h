@@ -29,6 +29,14 @@ struct DecodeResult {
   bool cudaFailed{false};
 };
 
+// Optional host<->device staging folded into the chunk pipeline (needs a host `frames` array).
+struct HostStaging {
+  const uint8_t* hostSrc{nullptr};  // host copy of the source buffer, same offsets as dSrc: chunk ranges are uploaded
+  uint8_t* hostDst{nullptr};        // receives device output bytes [dstSkip, dstSkip + dstSize)
+  uint64_t dstSkip{0};
+  uint64_t dstSize{~0ull};
+};
+
 // Parsed fixed header of a ZRA archive (source/zra.cpp:111-134 layout).
 struct ArchiveInfo {
   uint32_t headerSize;  // fixed + meta + table
@@ -60,10 +68,18 @@ class GpuContext {
 
   // Decodes frames described either by a host array (`frames`) or, when frames == nullptr, by the
   // seek table of a device-resident archive (`info`, firstFrame, dstBase). Synchronous.
+  // The frames are cut into chunks that run on a pool of streams: the phases of different chunks
+  // (entropy decode is latency-bound, sequence execution is issue-bound) overlap on the SMs, and
+  // with `io` the PCIe copies of one chunk overlap the kernels of the others.
   DecodeResult decode(const void* dSrc, size_t srcSize, const HostFrame* frames, const ArchiveInfo* info, uint64_t firstFrame,
-                      uint64_t nFrames, uint32_t maxDstCap, void* dDst, uint32_t* frameSizes, cudaStream_t st);
+                      uint64_t nFrames, uint32_t maxDstCap, void* dDst, uint32_t* frameSizes, cudaStream_t st,
+                      const HostStaging* io = nullptr);
 
   void bind();  // cudaSetDevice(device_)
+
+  // Per-kernel event timing (off by default; adds an event record per launch when on).
+  void set_profiling(bool on) { profiling_ = on; }
+  KernelTimer timer;
 
  private:
   int device_{0};
@@ -71,6 +87,12 @@ class GpuContext {
   cudaStream_t stream_{nullptr};
   std::string lastError_;
   uint64_t launches_{0};
+  bool profiling_{false};
+  static constexpr int kPoolStreams = 16;
+  cudaStream_t pool_[kPoolStreams] = {};
+  cudaEvent_t forkEvent_{nullptr};
+  uint32_t* summaryHost_{nullptr};  // pinned, 4 words per chunk
+  static constexpr uint32_t kMaxChunks = 1024;
 };
 
 // Thread-local default context used by the zra.h / zra.hpp host-pointer entry points.

@@ -43,14 +43,31 @@ OpStatus host_decompress_archive(GpuContext* g, const uint8_t* archive, size_t n
   uint8_t* dIn = static_cast<uint8_t*>(g->ensure(g->stageIn, pad4(n) + 16));
   uint8_t* dOut = static_cast<uint8_t*>(g->ensure(g->stageOut, info.uncompressedSize + 16));
   if (!dIn || !dOut) return cuda_failed();
-  if (g->check(cudaMemcpyAsync(dIn, archive, n, cudaMemcpyHostToDevice, st), "archive upload")) return cuda_failed();
+  // descriptors from the host copy of the seek table; the chunk pipeline uploads each chunk's
+  // compressed range, decodes it and downloads its output while other chunks are in flight
+  const uint8_t* table = archive + 38 + info.metaSize;
+  std::vector<HostFrame> frames(info.frames);
+  uint64_t prev = get_le(table, 5);
+  for (uint64_t f = 0; f < info.frames; f++) {
+    uint64_t next = get_le(table + kEntrySize * (f + 1), 5);
+    HostFrame& d = frames[f];
+    uint64_t begin = f * info.frameSize;
+    d.srcOff = info.headerSize + prev;
+    d.dstOff = begin;
+    d.dstCap = (uint32_t)std::min<uint64_t>(info.frameSize, info.uncompressedSize - begin);
+    d.exact = 1;
+    d.pad = 0;
+    // an inconsistent entry decodes as a zero-length frame -> srcSize_wrong, like the device table reader
+    d.srcLen = (next < prev || info.headerSize + next > n || next - prev > 0xFFFFFFFFull) ? 0 : (uint32_t)(next - prev);
+    if (!d.srcLen) d.srcOff = info.headerSize;
+    prev = next;
+  }
   uint32_t maxCap = (uint32_t)std::min<uint64_t>(info.frameSize, info.uncompressedSize);
-  DecodeResult r = g->decode(dIn, n, nullptr, &info, 0, info.frames, maxCap, dOut, nullptr, st);
-  if (r.cudaFailed || r.zstd) return from_decode(r);
-  if (g->check(cudaMemcpyAsync(out, dOut, info.uncompressedSize, cudaMemcpyDeviceToHost, st), "output download") ||
-      g->check(cudaStreamSynchronize(st), "output download"))
-    return cuda_failed();
-  return OpStatus{};
+  HostStaging io;
+  io.hostSrc = archive;
+  io.hostDst = out;
+  DecodeResult r = g->decode(dIn, n, frames.data(), nullptr, 0, info.frames, maxCap, dOut, nullptr, st, &io);
+  return from_decode(r);
 }
 
 OpStatus host_decode_frames(GpuContext* g, const uint8_t* src, size_t srcSize, const HostFrame* frames, size_t nFrames,
@@ -67,14 +84,13 @@ OpStatus host_decode_frames(GpuContext* g, const uint8_t* src, size_t srcSize, c
   uint8_t* dIn = static_cast<uint8_t*>(g->ensure(g->stageIn, pad4(srcSize) + 16));
   uint8_t* dOut = static_cast<uint8_t*>(g->ensure(g->stageOut, staged + 16));
   if (!dIn || !dOut) return cuda_failed();
-  if (g->check(cudaMemcpyAsync(dIn, src, srcSize, cudaMemcpyHostToDevice, st), "frame upload")) return cuda_failed();
-  DecodeResult r = g->decode(dIn, srcSize, frames, nullptr, 0, nFrames, maxCap, dOut, nullptr, st);
-  if (r.cudaFailed || r.zstd) return from_decode(r);
   if (skip + size > staged) return zra_error(5);
-  if (size && (g->check(cudaMemcpyAsync(out, dOut + skip, size, cudaMemcpyDeviceToHost, st), "output download") ||
-               g->check(cudaStreamSynchronize(st), "output download")))
-    return cuda_failed();
-  return OpStatus{};
+  HostStaging io;
+  io.hostSrc = src;
+  io.hostDst = out;
+  io.dstSkip = skip;
+  io.dstSize = size;
+  return from_decode(g->decode(dIn, srcSize, frames, nullptr, 0, nFrames, maxCap, dOut, nullptr, st, &io));
 }
 
 OpStatus host_decompress_range(GpuContext* g, const uint8_t* archive, size_t n, const ArchiveInfo& info, uint64_t offset,

@@ -59,6 +59,19 @@ const char* ZraCudaGetLastError(ZraCudaContext* context) { return context->gpu.l
 
 uint64_t ZraCudaGetLaunchCount(ZraCudaContext* context) { return context->gpu.launches(); }
 
+void ZraCudaSetProfiling(ZraCudaContext* context, int enabled) {
+  context->gpu.set_profiling(enabled != 0);
+  context->gpu.timer.reset();
+}
+
+int ZraCudaGetKernelProfile(ZraCudaContext* context, int index, const char** name, double* totalMs, uint64_t* launches) {
+  if (index < 1 || index >= K_COUNT) return 0;
+  *name = kernel_name(index);
+  *totalMs = context->gpu.timer.ms[index];
+  *launches = context->gpu.timer.launches[index];
+  return 1;
+}
+
 ZraStatus ZraCudaDecodeFrames(ZraCudaContext* context, const void* dSrc, size_t srcSize, const ZraCudaFrame* frames, uint32_t count,
                               void* dDst, uint32_t* frameSizes, uint32_t* failedFrame, void* stream) {
   GpuContext& g = context->gpu;
