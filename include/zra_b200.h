@@ -71,6 +71,17 @@ ZRA_EXPORT ZraStatus ZraCudaDecompressFrames(ZraCudaContext* context, const void
                                              uint64_t firstFrame, uint64_t frameCount, void* dOutput, size_t outputCapacity,
                                              void* stream);
 
+/* zra::CompressBuffer (source/zra.cpp:194-234) with input and archive resident in HBM: every frame
+ * is compressed by the GPU encoder (zstd levels 1-3 semantics; level 0 = 3, higher levels use the
+ * strongest implemented parser), the 40-bit seek table is the device prefix scan of the frame sizes
+ * and the header CRC-32 is computed on the device. outputCapacity must be at least
+ * ZraGetCompressedOutputBufferSize(inputSize, frameSize) + metaSize. Unlike the host entry point this
+ * one stores the metadata bytes (it does not reproduce the reference's metadata quirk).
+ * The input allocation must be readable up to 8 bytes past inputSize. */
+ZRA_EXPORT ZraStatus ZraCudaCompressBuffer(ZraCudaContext* context, const void* dInput, size_t inputSize, void* dOutput,
+                                           size_t outputCapacity, size_t* outputSize, int8_t compressionLevel, uint32_t frameSize,
+                                           bool checksum, const void* metaBuffer, size_t metaSize, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,142 @@
+"""GPU parity tests of the ENCODE path through the C-ABI: archives written by the CUDA encoder must
+round-trip bit-exactly through the reference decoder, the oracle and stock zstd, carry a
+byte-identical header / seek-table layout, and stay within 3 % of the reference's ratio."""
+import numpy as np
+import pytest
+
+import refzra
+import zra_b200
+from common import parse_header, seek_table
+from zra_b200 import synth
+
+pytestmark = pytest.mark.gpu
+needs_ref = pytest.mark.skipif(not refzra.have_ref(), reason="oracle/_ref not present")
+
+
+def make(kind, n, fs, seed=1):
+    if kind == "text":
+        return synth.text(n, seed=seed, threads=4)
+    if kind == "mixed":
+        return synth.mixed(n, period=fs, threads=4)
+    if kind == "random":
+        return synth.random_bytes(n, seed=seed, threads=4)
+    if kind == "zeros":
+        return np.zeros(n, np.uint8)
+    raise ValueError(kind)
+
+
+def check_archive(z, data, fs):
+    h = parse_header(z)
+    n = data.size
+    table = n // fs + (2 if n % fs else 1)
+    assert h["frameId"] == 0x184D2A50 and h["magic"] == 0x3041525A and h["version"] == 1
+    assert h["uncompressedSize"] == n and h["frameSize"] == fs and h["tableSize"] == table and h["metaSize"] == 0
+    assert h["headerSize"] == 38 + 5 * table - 8
+    t = seek_table(z)
+    assert t[0] == 0 and np.all(np.diff(t.astype(np.int64)) > 0) if n else True
+    assert h["size"] + int(t[-1]) == z.size
+    assert refzra.oracle().zra_oracle_header_crc(refzra._p(z), z.size) == h["hash"]
+    assert np.array_equal(refzra.oracle_decompress_buffer(z), data)
+    assert np.array_equal(refzra.system_zstd_decompress(z, n), data)
+    if refzra.have_ref():
+        assert np.array_equal(refzra.ref_decompress(z), data)
+
+
+@pytest.mark.parametrize("kind,n,fs,lvl,ck", [
+    ("text", 1_000_003, 16384, 3, True),
+    ("text", 4 << 20, 65536, 1, True),
+    ("text", 4 << 20, 65536, 2, False),
+    ("text", 4 << 20, 65536, 3, True),
+    ("text", (3 << 20) + 77, 262144, 3, True),
+    ("mixed", 4 << 20, 65536, 3, True),
+    ("random", 1 << 20, 65536, 3, True),
+    ("zeros", 2 << 20, 65536, 3, True),
+    ("zeros", 2 << 20, 262144, 1, True),
+    ("text", 100_000, 1000, 3, True),
+    ("text", 5, 16384, 3, True),
+    ("text", 1, 16384, 0, False),
+    ("text", 0, 16384, 3, True),
+    ("text", 700_000, 700_000, 3, True),
+    ("text", 300_000, 1 << 20, -5, True),
+    ("text", 1 << 20, 65536, 9, True),
+])
+def test_compress_buffer_roundtrip(kind, n, fs, lvl, ck):
+    data = make(kind, n, fs)
+    z = zra_b200.CompressBuffer(data, lvl, fs, ck)
+    check_archive(z, data, fs)
+    # and our own decoder
+    assert np.array_equal(zra_b200.DecompressBuffer(z), data)
+    if n > 10:
+        assert np.array_equal(zra_b200.DecompressRA(z, n // 3, min(5000, n - n // 3 - 1)), data[n // 3: n // 3 + min(5000, n - n // 3 - 1)])
+
+
+@needs_ref
+@pytest.mark.parametrize("kind,fs,lvl", [("text", 16384, 3), ("text", 65536, 1), ("text", 65536, 2), ("text", 65536, 3),
+                                         ("text", 262144, 3), ("mixed", 65536, 1), ("mixed", 65536, 3), ("text", 16384, 1)])
+def test_ratio_within_3_percent_of_reference(kind, fs, lvl):
+    n = 16 << 20
+    data = make(kind, n, fs, seed=fs + lvl)
+    ours = zra_b200.CompressBuffer(data, lvl, fs, True)
+    ref = refzra.ref_compress_mt(data, lvl, fs, True)
+    assert np.array_equal(refzra.ref_decompress(ours), data)
+    delta = ours.size / ref.size - 1
+    assert abs(delta) < 0.03, (ours.size, ref.size, delta)
+    # the headers have the same length and, apart from hash and table values, the same bytes
+    ho, hr = parse_header(ours), parse_header(ref)
+    for k in ("frameId", "headerSize", "magic", "version", "uncompressedSize", "tableSize", "frameSize", "metaSize"):
+        assert ho[k] == hr[k], k
+
+
+def test_metadata_quirk_of_the_reference_is_reproduced():
+    """zra::CompressBuffer records metaSize but stores no metadata; so do we."""
+    data = make("text", 200_000, 16384)
+    z = zra_b200.CompressBuffer(data, 3, 16384, True, meta=b"hello-meta")
+    h = parse_header(z)
+    assert h["metaSize"] == 10 and h["headerSize"] == 38 + 10 + 5 * h["tableSize"] - 8
+    if refzra.have_ref():
+        r = refzra.ref_compress(data, 3, 16384, True, meta=b"hello-meta")
+        hr = parse_header(r)
+        assert (hr["metaSize"], hr["headerSize"], hr["tableSize"]) == (h["metaSize"], h["headerSize"], h["tableSize"])
+
+
+def test_streaming_compressor_matches_buffer_api_and_handles_metadata():
+    fs = 16384
+    data = make("text", 10 * fs + 1234, fs)
+    c = zra_b200.Compressor(data.size, 3, fs, True, meta=b"\x01\x02\x03")
+    with pytest.raises(zra_b200.ZraError) as e:
+        c.GetHeader()
+    assert e.value.code == zra_b200.StatusCode.HeaderIncomplete
+    with pytest.raises(zra_b200.ZraError) as e:
+        c.Compress(data[: fs + 1])  # not frame aligned and not the end
+    assert e.value.code == zra_b200.StatusCode.InputFrameSizeMismatch
+    parts = [c.Compress(data[: 4 * fs]), c.Compress(data[4 * fs: 9 * fs]), c.Compress(data[9 * fs:])]
+    header = c.GetHeader()
+    assert header.size == c.GetHeaderSize() == 38 + 3 + 5 * 12
+    archive = np.concatenate([header] + parts)
+    assert zra_b200.Header(archive).GetMetadata() == b"\x01\x02\x03"
+    assert np.array_equal(refzra.oracle_decompress_buffer(archive), data)
+    assert np.array_equal(zra_b200.DecompressBuffer(archive), data)
+    if refzra.have_ref():
+        assert np.array_equal(refzra.ref_decompress(archive), data)
+    # frame bytes equal those of the one-shot API
+    one = zra_b200.CompressBuffer(data, 3, fs, True)
+    assert np.array_equal(np.concatenate(parts), one[parse_header(one)["size"]:])
+
+
+def test_device_compress_with_metadata(tmp_path):
+    import torch
+
+    ctx = zra_b200.CudaContext(0)
+    fs = 65536
+    data = make("text", (2 << 20) + 99, fs)
+    d_in = torch.zeros(data.size + 64, dtype=torch.uint8, device="cuda")
+    d_in[: data.size] = torch.from_numpy(data).cuda()
+    cap = zra_b200.GetOutputBufferSize(data.size, fs, 7) + 64
+    d_out = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+    n = ctx.compress_buffer(d_in.data_ptr(), data.size, d_out.data_ptr(), cap, 3, fs, True, b"abcdefg", torch.cuda.current_stream().cuda_stream)
+    z = d_out[:n].cpu().numpy()
+    h = parse_header(z)
+    assert h["metaSize"] == 7 and bytes(z[38:45]) == b"abcdefg"
+    assert np.array_equal(refzra.oracle_decompress_buffer(z), data)
+    if refzra.have_ref():
+        assert np.array_equal(refzra.ref_decompress(z), data)

@@ -103,6 +103,7 @@ def lib():
         "ZraCudaDecodeFrames": (ZraStatus, [vp, vp, sz, P(CudaFrame), u32, vp, P(u32), P(u32), vp]),
         "ZraCudaDecompressBuffer": (ZraStatus, [vp, vp, sz, vp, sz, vp]),
         "ZraCudaDecompressFrames": (ZraStatus, [vp, vp, sz, u64, u64, vp, sz, vp]),
+        "ZraCudaCompressBuffer": (ZraStatus, [vp, vp, sz, vp, sz, P(sz), C.c_int8, u32, C.c_bool, vp, sz, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -342,6 +343,14 @@ class CudaContext:
     def decompress_frames(self, d_archive, archive_size, first_frame, frame_count, d_out, out_capacity, stream=0):
         self._raise(lib().ZraCudaDecompressFrames(self._c, C.c_void_p(d_archive), archive_size, first_frame, frame_count,
                                                   C.c_void_p(d_out), out_capacity, C.c_void_p(stream)))
+
+    def compress_buffer(self, d_in, in_size, d_out, out_capacity, level=0, frame_size=16384, checksum=True, meta=b"", stream=0):
+        """Device-resident CompressBuffer; returns the archive size."""
+        m = _as_array(meta)
+        n = C.c_size_t(0)
+        self._raise(lib().ZraCudaCompressBuffer(self._c, C.c_void_p(d_in), in_size, C.c_void_p(d_out), out_capacity, C.byref(n), level,
+                                                frame_size, checksum, _ptr(m), m.size, C.c_void_p(stream)))
+        return n.value
 
     def __del__(self):
         if getattr(self, "_c", None):

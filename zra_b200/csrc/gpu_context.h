@@ -75,6 +75,21 @@ class GpuContext {
                       uint64_t nFrames, uint32_t maxDstCap, void* dDst, uint32_t* frameSizes, cudaStream_t st,
                       const HostStaging* io = nullptr);
 
+  // Compression results.
+  struct CompressStatus {
+    bool cudaFailed{false};
+    int zra{0};           // zra::StatusCode value (0 ok, 6 output too small, 7 compressed size too large)
+    uint64_t total{0};    // bytes produced
+  };
+  // dIn[0..n) -> complete archive at dOut (header, metadata, 40-bit seek table, frames), all on the device.
+  // refMetaQuirk reproduces zra::CompressBuffer's layout for a non-empty meta: the
+  // header records metaSize but no metadata bytes are stored.
+  CompressStatus compress_archive(const void* dIn, size_t n, void* dOut, size_t outCap, int level, uint32_t frameSize,
+                                  bool checksum, const uint8_t* metaHost, size_t metaSize, bool refMetaQuirk, cudaStream_t st);
+  // dIn[0..n) -> zstd frames back to back at dOut (no header); sizesHost[i] = compressed size of frame i.
+  CompressStatus compress_frames(const void* dIn, size_t n, uint32_t frameSize, int level, bool checksum, void* dOut,
+                                 size_t outCap, uint64_t* sizesHost, cudaStream_t st);
+
   void bind();  // cudaSetDevice(device_)
 
   // Per-kernel event timing (off by default; adds an event record per launch when on).

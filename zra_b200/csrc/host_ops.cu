@@ -119,13 +119,42 @@ OpStatus host_decompress_range(GpuContext* g, const uint8_t* archive, size_t n, 
                             offset - first * info.frameSize, size, out);
 }
 
-OpStatus host_compress_buffer(GpuContext*, const uint8_t*, size_t, uint8_t*, size_t, size_t*, int, uint32_t, bool, const uint8_t*,
-                              size_t) {
-  return zra_error(1, 1);
+OpStatus host_compress_buffer(GpuContext* g, const uint8_t* in, size_t n, uint8_t* out, size_t outCap, size_t* written, int level,
+                              uint32_t frameSize, bool checksum, const uint8_t* meta, size_t metaSize) {
+  cudaStream_t st = g->stream();
+  uint8_t* dIn = static_cast<uint8_t*>(g->ensure(g->stageIn, pad4(n) + 64));
+  uint8_t* dOut = static_cast<uint8_t*>(g->ensure(g->stageOut, outCap + 64));
+  if (!dIn || !dOut) return cuda_failed();
+  if (n && g->check(cudaMemcpyAsync(dIn, in, n, cudaMemcpyHostToDevice, st), "input upload")) return cuda_failed();
+  // zero the slack the 32-bit readers may touch past the end of the input
+  if (g->check(cudaMemsetAsync(dIn + n, 0, pad4(n) + 64 - n, st), "memset")) return cuda_failed();
+  GpuContext::CompressStatus r = g->compress_archive(dIn, n, dOut, outCap, level, frameSize, checksum, meta, metaSize,
+                                                     /*refMetaQuirk=*/true, st);
+  if (r.cudaFailed) return cuda_failed();
+  if (r.zra) return zra_error(r.zra);
+  if (g->check(cudaMemcpyAsync(out, dOut, r.total, cudaMemcpyDeviceToHost, st), "archive download") ||
+      g->check(cudaStreamSynchronize(st), "archive download"))
+    return cuda_failed();
+  *written = r.total;
+  return OpStatus{};
 }
 
-OpStatus host_compress_frames(GpuContext*, const uint8_t*, size_t, uint32_t, int, bool, uint8_t*, size_t, uint64_t*, size_t*) {
-  return zra_error(1, 1);
+OpStatus host_compress_frames(GpuContext* g, const uint8_t* in, size_t n, uint32_t frameSize, int level, bool checksum, uint8_t* out,
+                              size_t outCap, uint64_t* sizes, size_t* produced) {
+  cudaStream_t st = g->stream();
+  uint8_t* dIn = static_cast<uint8_t*>(g->ensure(g->stageIn, pad4(n) + 64));
+  uint8_t* dOut = static_cast<uint8_t*>(g->ensure(g->stageOut, outCap + 64));
+  if (!dIn || !dOut) return cuda_failed();
+  if (n && g->check(cudaMemcpyAsync(dIn, in, n, cudaMemcpyHostToDevice, st), "input upload")) return cuda_failed();
+  if (g->check(cudaMemsetAsync(dIn + n, 0, pad4(n) + 64 - n, st), "memset")) return cuda_failed();
+  GpuContext::CompressStatus r = g->compress_frames(dIn, n, frameSize, level, checksum, dOut, outCap, sizes, st);
+  if (r.cudaFailed) return cuda_failed();
+  if (r.zra) return zra_error(r.zra);
+  if (r.total && (g->check(cudaMemcpyAsync(out, dOut, r.total, cudaMemcpyDeviceToHost, st), "frames download") ||
+                  g->check(cudaStreamSynchronize(st), "frames download")))
+    return cuda_failed();
+  *produced = r.total;
+  return OpStatus{};
 }
 
 }  // namespace zrab

@@ -117,4 +117,22 @@ ZraStatus ZraCudaDecompressBuffer(ZraCudaContext* context, const void* dArchive,
   return from(g.decode(dArchive, archiveSize, nullptr, &info, 0, info.frames, maxCap, dOutput, nullptr, s));
 }
 
+ZraStatus ZraCudaCompressBuffer(ZraCudaContext* context, const void* dInput, size_t inputSize, void* dOutput, size_t outputCapacity,
+                                size_t* outputSize, int8_t compressionLevel, uint32_t frameSize, bool checksum, const void* metaBuffer,
+                                size_t metaSize, void* stream) {
+  GpuContext& g = context->gpu;
+  if (!g.ok()) return st(ZStdError, 1);
+  if (!frameSize) return st(ZStdError, 42);  // parameter_outOfBound
+  uint32_t table = table_entries(inputSize, frameSize);
+  size_t need = kFixedHeaderSize + metaSize + kEntrySize * (size_t)table + zstd_compress_bound(frameSize) * (size_t)(table - 1);
+  if (outputCapacity < need) return st(OutputBufferTooSmall);
+  GpuContext::CompressStatus r = g.compress_archive(dInput, inputSize, dOutput, outputCapacity, compressionLevel, frameSize, checksum,
+                                                    static_cast<const uint8_t*>(metaBuffer), metaSize, /*refMetaQuirk=*/false,
+                                                    static_cast<cudaStream_t>(stream));
+  if (r.cudaFailed) return st(ZStdError, 1);
+  if (r.zra) return st(static_cast<ZraStatusCode>(r.zra));
+  *outputSize = r.total;
+  return st(Success);
+}
+
 }  // extern "C"
