@@ -7,9 +7,10 @@
  * bench.py, a multi-GPU driver, a storage engine — skip the PCIe staging. Each function names
  * the reference code path it replaces.
  *
- * Alignment rule for every device source pointer: the base address must be 4-byte aligned and
- * the allocation must be readable up to the next multiple of 4 bytes past `size` (any
- * cudaMalloc / torch allocation satisfies this).
+ * Alignment rule for every device source pointer: the base address must be 16-byte aligned and
+ * the allocation must be readable up to the next multiple of 16 bytes past `size` (the decoder
+ * fetches compressed bytes in aligned 16-byte groups; any cudaMalloc / fresh torch allocation
+ * satisfies both).
  */
 #ifndef ZRA_B200_DEVICE_H
 #define ZRA_B200_DEVICE_H

@@ -43,8 +43,11 @@ extern "C" __attribute__((visibility("default"))) long long sim_decode_frames(co
         // scalar stand-in for seq_execute
         u8* op = out + c.blkDst;
         u32 litPos = 0;
+        u32 prevLit = 0, prevOut = 0;
         for (u32 i = 0; i < c.nbSeq; i++) {
-          u32 ll = seq_ll(seqs[i]), ml = seq_ml(seqs[i]), off = seq_off(seqs[i]);
+          // records are cumulative: (literals consumed, bytes regenerated) after sequence i
+          u32 ll = rec_lit_end(seqs[i]) - prevLit, ml = rec_out_end(seqs[i]) - prevOut - ll, off = rec_off(seqs[i]);
+          prevLit = rec_lit_end(seqs[i]); prevOut = rec_out_end(seqs[i]);
           for (u32 k = 0; k < ll; k++) {
             u8 b = c.litMode == LIT_HUF ? lit[litPos + k] : (c.litMode == LIT_RAW ? src[d.srcOff + c.litSrc + litPos + k] : (u8)c.litSrc);
             op[k] = b;

@@ -286,92 +286,224 @@ ZRA_DEV u32 huf_stream(const u8* srcBase, const FrameDesc& d, const FrameCtx& c,
 }
 
 // ---------------------------------------------------------------- seq_decode (1 thread / frame)
-// Packed sequence record: ll (18 bits) | ml (18 bits) << 18 | offset (28 bits) << 36.
+// Sequence records handed to seq_execute are CUMULATIVE, so the executor needs no prefix scans:
+//   litEnd (18 bits) | outEnd (18 bits) << 18 | offset (28 bits) << 36
+// litEnd = literals consumed by sequences 0..i of the block, outEnd = bytes regenerated by them
+// (both <= 128 KiB = 2^17, hence 18 bits), offset = the resolved match distance (repcodes done).
 ZRA_DEV u64 seq_pack(u32 ll, u32 ml, u32 off) { return (u64)ll | ((u64)ml << 18) | ((u64)off << 36); }
 ZRA_DEV u32 seq_ll(u64 s) { return (u32)s & 0x3FFFFu; }
 ZRA_DEV u32 seq_ml(u64 s) { return (u32)(s >> 18) & 0x3FFFFu; }
 ZRA_DEV u32 seq_off(u64 s) { return (u32)(s >> 36); }
+ZRA_DEV u32 rec_lit_end(u64 s) { return (u32)s & 0x3FFFFu; }
+ZRA_DEV u32 rec_out_end(u64 s) { return (u32)(s >> 18) & 0x3FFFFu; }
+ZRA_DEV u32 rec_off(u64 s) { return (u32)(s >> 36); }
 constexpr u32 kMaxOffset = (1u << 28) - 1;
+
+// Backward bit reader of the sequence stream, built for 32 unrelated streams advancing in
+// lock-step in one warp. SIMT facts that shape it (measured, profiles/r01b): a data-dependent
+// refill branch is taken by SOME lane at every step, so its body runs every step with two or
+// three lanes active; and a per-lane register prefetch does not work, because the scoreboard is
+// per warp — one lane's outstanding load stalls every other lane that touches the same register.
+// So the reader carries NO window between steps, only a bit position:
+//  * compressed bytes are staged in a small per-lane ring in shared memory (16 words, laid out
+//    [word][lane] so that a warp access is always bank-conflict free);
+//  * every step rebuilds a 64-bit window from three ring words at the current bit position
+//    (3 LDS + 2 funnel shifts, unconditional, no branch);
+//  * the ring is topped up warp-synchronously at "refill points" (every 2 steps): each lane
+//    issues at most one 16-byte LDG for its next group and stores the group it issued at the
+//    previous point — every lane issues and consumes at the same instruction, so the per-warp
+//    scoreboard never couples unrelated lanes, and the load has two steps to land.
+// Bit indices are absolute within the frame's "group space": group 0 is the 16-byte aligned
+// group that holds the stream's first byte, word w = 4*group + i. Unread bits are [b0, p).
+// Nothing is masked: an over-read consumes whatever lies below the stream (or stale ring words)
+// and is caught by p != b0 at the end of the block; garbage states stay inside their tables.
+constexpr u32 kRingWords = 16;
+
+struct SeqReader {
+  i32 p;                 // absolute index of the next unread bit, plus one
+  i32 b0;                // absolute index of the stream's first bit (0..127)
+  i32 loadedW;           // lowest word index present in the ring
+  i32 reqW;              // lowest word index requested (== loadedW when no group is in flight)
+  const u32* g0;         // address of group 0 (16-byte aligned)
+  u32 f0, f1, f2, f3;    // the group in flight (words reqW .. reqW+3)
+  u32* ring;             // this lane's ring: word w lives at ring[(w & 15) * stride]
+  u32 stride;
+
+  ZRA_DEV u32 ring_ld(i32 w) const { return ring[((u32)w & (kRingWords - 1)) * stride]; }
+  ZRA_DEV void ring_st(i32 w, u32 v) { ring[((u32)w & (kRingWords - 1)) * stride] = v; }
+  ZRA_DEV void fetch_group(i32 firstWord) {  // f <- words firstWord .. firstWord+3
+#if defined(__CUDA_ARCH__)
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(g0 + firstWord));
+    f0 = v.x; f1 = v.y; f2 = v.z; f3 = v.w;
+#else
+    f0 = g0[firstWord]; f1 = g0[firstWord + 1]; f2 = g0[firstWord + 2]; f3 = g0[firstWord + 3];
+#endif
+  }
+  ZRA_DEV void land() {  // the group in flight goes into the ring
+    if (reqW < loadedW) {
+      ring_st(reqW, f0); ring_st(reqW + 1, f1); ring_st(reqW + 2, f2); ring_st(reqW + 3, f3);
+      loadedW = reqW;
+    }
+  }
+  // Refill point. Between two points a lane consumes at most 4 words (2 steps x 64 bits); one
+  // group per point keeps at least 9 landed words ahead of the cursor.
+  ZRA_DEV void refill_point() {
+    land();
+    const i32 k = (p - 1) >> 5;
+    // safety net (never taken by streams whose steps stay within 64 bits): synchronous top-up
+    while (loadedW > 0 && k - loadedW < 6) {
+      reqW = loadedW - 4;
+      fetch_group(reqW);
+      land();
+    }
+    if (reqW > 0 && k - reqW + 5 <= (i32)kRingWords) {
+      reqW -= 4;
+      fetch_group(reqW);
+#if defined(__CUDA_ARCH__)
+      if (reqW >= 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(g0 + reqW - 8));
+#endif
+    }
+  }
+  // The stream is src[byteOff, byteOff+len); base must be 16-byte aligned and the buffer readable
+  // to the end of the 16-byte group that holds the stream's last byte.
+  ZRA_DEV bool init(const u8* base, u64 byteOff, u32 len, u32* ringMem, u32 ringStride) {
+    ring = ringMem; stride = ringStride;
+    if (len == 0) return false;
+    u32 last = base[byteOff + len - 1];
+    if (last == 0) return false;
+    const u8* first = base + byteOff;
+    const u8* grp = reinterpret_cast<const u8*>(reinterpret_cast<uintptr_t>(first) & ~(uintptr_t)15);
+    g0 = reinterpret_cast<const u32*>(grp);
+    b0 = (i32)(first - grp) * 8;
+    p = b0 + (i32)((len - 1) * 8 + highbit32(last));
+    // synchronous initial fill: the top groups, as many as the ring holds
+    const i32 topGroup = (p - 1 >= 0 ? (p - 1) : 0) >> 7;
+    i32 g = topGroup;
+    for (u32 n = 0; n < kRingWords / 4 && g >= 0; n++, g--) {
+      fetch_group(4 * g);
+      ring_st(4 * g, f0); ring_st(4 * g + 1, f1); ring_st(4 * g + 2, f2); ring_st(4 * g + 3, f3);
+    }
+    loadedW = reqW = 4 * (g + 1);
+    return true;
+  }
+  // 64-bit window at the cursor: bit 31 of hi is the next unread bit.
+  ZRA_DEV void window(u32& hi, u32& lo) const {
+    const i32 t = p - 1;
+    const i32 k = t >> 5;
+    const u32 s = ~(u32)t & 31u;
+    const u32 w0 = ring_ld(k), w1 = ring_ld(k - 1), w2 = ring_ld(k - 2);
+    hi = fsh_lc(w1, w0, s);
+    lo = fsh_lc(w2, w1, s);
+  }
+};
+
+// n <= 32 bits off the top of a 64-bit window (hi:lo)
+ZRA_DEV u32 win_take(u32& hi, u32& lo, u32 n) {
+  u32 v = fsh_lc(hi, 0, n);
+  hi = fsh_lc(lo, hi, n);
+  lo = fsh_lc(0, lo, n);
+  return v;
+}
 
 // Per-frame state of the sequence stage; lives in registers of the lane that owns the frame.
 struct SeqState {
-  BackReader br;
+  SeqReader br;
   u32 sLL, sML, sOF;       // FSE states
   u32 rep0, rep1, rep2;    // repeat-offset history
   u32 litUsed, produced;   // literals consumed / bytes regenerated so far in this block
   u32 i, n;                // sequence cursor / count
   u32 llLog, ofLog, mlLog;
   u32 litSize, room, blkDst;
+  u32 err;                 // first error seen (sticky), ZErr
 };
 
 // Starts the sequence stage of the current block of one frame. Returns 0 or a ZErr.
-ZRA_DEV u32 seq_begin(const u8* srcBase, const FrameDesc& d, const FrameCtx& c, u32 seqCap, SeqState& s) {
+ZRA_DEV u32 seq_begin(const u8* srcBase, const FrameDesc& d, const FrameCtx& c, u32 seqCap, SeqState& s, u32* ringMem,
+                      u32 ringStride) {
   if (c.nbSeq > seqCap) return ZE_CORRUPTION;
-  if (!s.br.init(srcBase, d.srcOff + c.seqOff, c.seqLen)) return ZE_CORRUPTION;
+  if (!s.br.init(srcBase, d.srcOff + c.seqOff, c.seqLen, ringMem, ringStride)) return ZE_CORRUPTION;
   s.llLog = c.llLog; s.ofLog = c.ofLog; s.mlLog = c.mlLog;
-  s.sLL = s.br.read(s.llLog);
-  s.sOF = s.br.read(s.ofLog);
-  s.br.refill();
-  s.sML = s.br.read(s.mlLog);
+  u32 hi, lo;
+  s.br.window(hi, lo);
+  s.sLL = win_take(hi, lo, s.llLog);
+  s.sOF = win_take(hi, lo, s.ofLog);
+  s.sML = win_take(hi, lo, s.mlLog);
+  s.br.p -= (i32)(s.llLog + s.ofLog + s.mlLog);
   s.rep0 = c.rep[0]; s.rep1 = c.rep[1]; s.rep2 = c.rep[2];
   s.litUsed = 0; s.produced = 0; s.i = 0; s.n = c.nbSeq;
   s.litSize = c.litSize; s.room = d.dstCap - c.blkDst; s.blkDst = c.blkDst;
+  s.err = 0;
   return ZE_OK;
 }
 
-// Decodes and validates ONE sequence. tLL/tML/tOF are the compact tables (shared memory in the
-// kernel), lutLL/lutML the packed baseline tables. Returns 0 or a ZErr; *rec receives the record.
-ZRA_DEV u32 seq_step(const CSym* tLL, const CSym* tML, const CSym* tOF, const u32* lutLL, const u32* lutML, SeqState& s, u64* rec) {
-  BackReader& br = s.br;
+// Decodes and validates ONE sequence, completely branch-free in the common case (lanes of a warp
+// run this in lock-step on unrelated frames, so every data-dependent branch would serialise).
+// tLL/tML/tOF are the compact tables (shared memory in the kernel), lutLL/lutML the packed
+// baseline tables. Errors are sticky in s.err (the first one wins, in the reference's order of
+// checks); decoding simply continues on garbage, which cannot leave the tables or the record
+// array. Reference: ZSTD_decodeSequence, zstd/decompress/zstd_decompress_block.c:838-948.
+ZRA_DEV u64 seq_step(const CSym* tLL, const CSym* tML, const CSym* tOF, const u32* lutLL, const u32* lutML, SeqState& s) {
+  SeqReader& br = s.br;
+  u32 hi, lo;
+  br.window(hi, lo);
   const u32 eLL = tLL[s.sLL], eML = tML[s.sML], eOF = tOF[s.sOF];
-  const u32 lutl = lutLL[csym_symbol((CSym)eLL)], lutm = lutML[csym_symbol((CSym)eML)];
-  const u32 ofBits = csym_symbol((CSym)eOF);
+  const u32 lutl = lutLL[eLL & 63u], lutm = lutML[eML & 63u];
+  const u32 ofc = eOF & 63u;
   const u32 llBase = lutl & 0xFFFFFFu, llBits = lutl >> 24;
   const u32 mlBase = lutm & 0xFFFFFFu, mlBits = lutm >> 24;
-  u32 offset;
-  br.refill();
-  if (ofBits > 1) {
-    offset = of_base(ofBits) + br.read(ofBits);
-    s.rep2 = s.rep1; s.rep1 = s.rep0; s.rep0 = offset;
-  } else {
-    u32 ll0 = (llBase == 0);
-    if (ofBits == 0) {
-      if (!ll0) offset = s.rep0;
-      else { offset = s.rep1; s.rep1 = s.rep0; s.rep0 = offset; }
-    } else {
-      u32 idx = 1 + ll0 + br.read(1);
-      u32 v = (idx == 3) ? s.rep0 - 1 : (idx == 1 ? s.rep1 : s.rep2);
-      v += !v;
-      if (idx != 1) s.rep2 = s.rep1;
-      s.rep1 = s.rep0; s.rep0 = offset = v;
-    }
+  // next-state parameters: nbBits = log - highbit(ns), base = (ns << nbBits) - tableSize
+  const u32 keep = (s.i + 1 < s.n) ? 0xFFFFFFFFu : 0u;  // the last sequence leaves the states alone
+  const u32 nsLL = eLL >> 6, nsML = eML >> 6, nsOF = eOF >> 6;
+  const u32 nbLL = (s.llLog - highbit32(nsLL)) & keep;
+  const u32 nbML = (s.mlLog - highbit32(nsML)) & keep;
+  const u32 nbOF = (s.ofLog - highbit32(nsOF)) & keep;
+  // ---- bits, in stream order: offset extra | match extra | literal extra | LL, ML, OF state bits
+  const u32 extra = ofc + mlBits + llBits;        // <= 31 + 16 + 16
+  const u32 stateBits = nbLL + nbML + nbOF;       // <= 26
+  const u32 ofx = win_take(hi, lo, ofc);
+  const u32 mlx = win_take(hi, lo, mlBits);
+  const u32 llx = win_take(hi, lo, llBits);
+  if (extra + stateBits > 64) {  // cannot happen below 2^25-byte windows with sane lengths: second window for the states
+    br.p -= (i32)extra;
+    br.window(hi, lo);
+    br.p += (i32)extra;
   }
-  br.refill();
-  const u32 ml = mlBase + br.read(mlBits);
-  const u32 ll = llBase + br.read(llBits);
-  br.refill();
-  if (s.i + 1 < s.n) {  // the last sequence leaves the states alone
-    u32 ns = csym_ns((CSym)eLL), nb = s.llLog - highbit32(ns);
-    s.sLL = (ns << nb) - (1u << s.llLog) + br.read(nb);
-    ns = csym_ns((CSym)eML); nb = s.mlLog - highbit32(ns);
-    s.sML = (ns << nb) - (1u << s.mlLog) + br.read(nb);
-    ns = csym_ns((CSym)eOF); nb = s.ofLog - highbit32(ns);
-    s.sOF = (ns << nb) - (1u << s.ofLog) + br.read(nb);
-  }
+  const u32 bLL = win_take(hi, lo, nbLL);
+  const u32 bML = win_take(hi, lo, nbML);
+  const u32 bOF = win_take(hi, lo, nbOF);
+  br.p -= (i32)(extra + stateBits);
+  s.sLL = ((nsLL << nbLL) - (1u << s.llLog) + bLL) & keep;
+  s.sML = ((nsML << nbML) - (1u << s.mlLog) + bML) & keep;
+  s.sOF = ((nsOF << nbOF) - (1u << s.ofLog) + bOF) & keep;
+  // ---- offset: new value or one of the three repeat offsets (zstd_decompress_block.c:871-888)
+  const u32 ll = llBase + llx, ml = mlBase + mlx;
+  const u32 ll0 = (llBase == 0);
+  const bool isRep = ofc <= 1;
+  const u32 idx = ofc + ofx + ll0;                      // only meaningful when isRep: 0..3
+  const u32 newOff = (1u << (ofc & 31u)) - 3u + ofx;    // only meaningful when !isRep
+  u32 repv = idx == 0 ? s.rep0 : (idx == 1 ? s.rep1 : (idx == 2 ? s.rep2 : s.rep0 - 1u));
+  repv += !repv;
+  const u32 offset = isRep ? repv : newOff;
+  if (!isRep || idx >= 2) s.rep2 = s.rep1;
+  if (!isRep || idx >= 1) s.rep1 = s.rep0;
+  s.rep0 = offset;
+  // ---- validation: everything seq_execute will trust
+  const u32 litEnd = s.litUsed + ll;
+  const u32 outEnd = s.produced + ll + ml;
+  u32 e = 0;
+  if (offset > s.blkDst + s.produced + ll || offset > kMaxOffset) e = ZE_CORRUPTION;
+  if (ll + ml > s.room - s.produced) e = ZE_DST_TOO_SMALL;  // produced <= room is an invariant while err == 0
+  if (ll > s.litSize - s.litUsed) e = ZE_CORRUPTION;
+  if (!s.err) s.err = e;
+  if (!e) { s.litUsed = litEnd; s.produced = outEnd; }   // keeps the invariants (and the record fields) in range
   s.i++;
-  // validation: everything seq_execute will trust
-  if (ll > s.litSize - s.litUsed) return ZE_CORRUPTION;
-  s.litUsed += ll;
-  if (ll + ml > s.room - s.produced) return ZE_DST_TOO_SMALL;  // produced <= room is an invariant
-  if (offset > s.blkDst + s.produced + ll || offset > kMaxOffset) return ZE_CORRUPTION;
-  s.produced += ll + ml;
-  *rec = seq_pack(ll, ml, offset);
-  return ZE_OK;
+  return (u64)(litEnd & 0x3FFFFu) | ((u64)(outEnd & 0x3FFFFu) << 18) | ((u64)(offset & kMaxOffset) << 36);
 }
 
 // Finishes the block after its last sequence: stream exhaustion, trailing literals, write-back.
 ZRA_DEV u32 seq_end(const SeqState& s, FrameCtx& c) {
-  if (s.br.remaining != 0) return ZE_CORRUPTION;
+  if (s.err) return s.err;
+  if (s.br.p != s.br.b0) return ZE_CORRUPTION;
   u32 lastLits = s.litSize - s.litUsed;
   if (lastLits > s.room - s.produced) return ZE_DST_TOO_SMALL;
   c.rep[0] = s.rep0; c.rep[1] = s.rep1; c.rep[2] = s.rep2;
@@ -383,15 +515,14 @@ ZRA_DEV u32 seq_end(const SeqState& s, FrameCtx& c) {
 // Whole stage for one frame, thread-serial (host logic tests; the kernel interleaves 32 frames).
 ZRA_DEV void seq_decode(const u8* srcBase, const FrameDesc& d, FrameCtx& c, const FrameTables& t, u64* seqs, u32 seqCap) {
   if (c.blkType != BT_COMPRESSED || c.status || !c.nbSeq) return;
-  u32 lutLL[36], lutML[53];
-  for (u32 k = 0; k < 36; k++) lutLL[k] = ll_lut(k);
-  for (u32 k = 0; k < 53; k++) lutML[k] = ml_lut(k);
+  u32 lutLL[64], lutML[64], ring[kRingWords];
+  for (u32 k = 0; k < 64; k++) { lutLL[k] = k < 36 ? ll_lut(k) : 0; lutML[k] = k < 53 ? ml_lut(k) : 0; }
   SeqState s;
-  u32 err = seq_begin(srcBase, d, c, seqCap, s);
+  u32 err = seq_begin(srcBase, d, c, seqCap, s, ring, 1);
   while (!err && s.i < s.n) {
-    u64 rec;
-    err = seq_step(t.ll, t.ml, t.of, lutLL, lutML, s, &rec);
-    if (!err) seqs[s.i - 1] = rec;
+    if ((s.i & 1) == 0) s.br.refill_point();   // same cadence as the kernel: a refill point every 2 steps
+    u64 rec = seq_step(t.ll, t.ml, t.of, lutLL, lutML, s);
+    seqs[s.i - 1] = rec;
   }
   if (!err) err = seq_end(s, c);
   if (err) frame_fail(c, err);

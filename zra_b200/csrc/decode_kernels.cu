@@ -180,13 +180,17 @@ __global__ void __launch_bounds__(32) k_huf_decode(const u8* __restrict__ src, c
 }
 
 // ------------------------------------------------------------------------------------------
-// FSE sequences. One warp = 32 frame slots, one lane per frame; all 32 decode one sequence per
-// iteration in lock-step from tables in shared memory. A lane that finishes its frame pulls the
-// next one from the work list, and the warp copies that frame's tables in cooperatively.
+// FSE sequences. One lane per frame; the warp's 32 frames decode one sequence per iteration in
+// lock-step with their three compact FSE tables in shared memory (2.5 KiB per frame, 88 frames per
+// SM). The step itself (decode_core.cuh: seq_step) is branch-free; the inner loop runs a
+// warp-uniform number of steps (the minimum left over the active lanes), so there is no per-step
+// completion test. A lane that finishes its frame pulls the next one from the work list and the
+// warp copies that frame's tables in cooperatively.
 constexpr u32 kSeqSlotEntries = 1280;  // ll 512 + ml 512 + of 256
-constexpr u32 kSeqSlots = 88;          // frames resident per CTA: 88 x 2560 B + LUTs = 225.7 KB of the SM's 227 KB
+constexpr u32 kSeqSlots = 88;          // frames resident per CTA: 88 x 2560 B + LUTs = 220.5 KiB of the SM's 227 KiB
 constexpr u32 kSeqThreads = 96;        // three warps; lanes 88..95 idle
-constexpr u32 kSeqWarpSmem = kSeqSlots * kSeqSlotEntries * sizeof(CSym) + (36 + 53 + 7) * sizeof(u32);
+constexpr u32 kSeqWarpSmem = kSeqSlots * kSeqSlotEntries * sizeof(CSym) + 128 * sizeof(u32) + kRingWords * kSeqThreads * sizeof(u32);
+static_assert(kSeqWarpSmem <= 227 * 1024, "k_seq_decode shared memory");
 
 __global__ void __launch_bounds__(kSeqThreads) k_seq_decode(const u8* __restrict__ src, const FrameDesc* __restrict__ descs,
                                                    FrameCtx* __restrict__ ctxs, const FrameTables* __restrict__ tabs,
@@ -195,10 +199,13 @@ __global__ void __launch_bounds__(kSeqThreads) k_seq_decode(const u8* __restrict
   extern __shared__ __align__(16) u8 smem[];
   CSym* slots = reinterpret_cast<CSym*>(smem);
   u32* lutLL = reinterpret_cast<u32*>(smem + kSeqSlots * kSeqSlotEntries * sizeof(CSym));
-  u32* lutML = lutLL + 36;
+  u32* lutML = lutLL + 64;
+  u32* ring = lutML + 64 + threadIdx.x;  // [kRingWords][kSeqThreads]: a warp access never conflicts
   const u32 lane = threadIdx.x & 31, slot = threadIdx.x, slotBase = threadIdx.x & ~31u;
-  for (u32 k = threadIdx.x; k < 36; k += kSeqThreads) lutLL[k] = ll_lut(k);
-  for (u32 k = threadIdx.x; k < 53; k += kSeqThreads) lutML[k] = ml_lut(k);
+  for (u32 k = threadIdx.x; k < 64; k += kSeqThreads) {
+    lutLL[k] = k < 36 ? ll_lut(k) : 0u;
+    lutML[k] = k < 53 ? ml_lut(k) : 0u;
+  }
   __syncthreads();  // the only block-wide barrier: from here on the warps run independently
   const CSym* tLL = slots + (slot < kSeqSlots ? slot : 0) * kSeqSlotEntries;
   const CSym* tML = tLL + 512;
@@ -207,8 +214,10 @@ __global__ void __launch_bounds__(kSeqThreads) k_seq_decode(const u8* __restrict
   bool active = false, exhausted = slot >= kSeqSlots;
   u32 frame = kNone;
   SeqState st;
+  st.i = 0; st.n = 0;
   u64* out = nullptr;
   for (;;) {
+    // ---- idle lanes pull frames; the warp stages their tables
     if (__any_sync(kFull, !active && !exhausted)) {
       u32 f = kNone;
       if (!active && !exhausted) {
@@ -223,13 +232,14 @@ __global__ void __launch_bounds__(kSeqThreads) k_seq_decode(const u8* __restrict
         u32 wf = __shfl_sync(kFull, f, who);
         const uint4* g = reinterpret_cast<const uint4*>(&tabs[wf]);
         uint4* d = reinterpret_cast<uint4*>(slots + (slotBase + who) * kSeqSlotEntries);
-        for (u32 k = lane; k < kSeqSlotEntries * sizeof(CSym) / 16; k += 32) d[k] = g[k];
+#pragma unroll
+        for (u32 k = 0; k < kSeqSlotEntries * sizeof(CSym) / 16 / 32; k++) d[lane + 32 * k] = __ldg(g + lane + 32 * k);
       }
       __syncwarp();
       if (f != kNone) {
         frame = f;
         out = seqs + (u64)f * seqStride;
-        u32 err = seq_begin(src, descs[f], ctxs[f], seqStride, st);
+        u32 err = seq_begin(src, descs[f], ctxs[f], seqStride, st, ring, kSeqThreads);
         if (err) {
           FrameCtx* g = &ctxs[f];
           if (!g->status) g->status = err;
@@ -244,90 +254,94 @@ __global__ void __launch_bounds__(kSeqThreads) k_seq_decode(const u8* __restrict
       if (__all_sync(kFull, exhausted)) break;
       continue;  // a lane whose frame failed to start fetches again
     }
+    // ---- run until the first active lane reaches the end of its block
+    const u32 steps = __reduce_min_sync(kFull, active ? st.n - st.i : 0xFFFFFFFFu);
+    if (active) {
 #pragma unroll 1
-    for (u32 rep = 0; rep < 4; rep++) {
-      if (active) {
-        u64 rec;
-        u32 err = seq_step(tLL, tML, tOF, lutLL, lutML, st, &rec);
-        if (!err) out[st.i - 1] = rec;
-        if (err || st.i == st.n) {
-          FrameCtx* g = &ctxs[frame];
-          if (!err) {
-            FrameCtx tmp;
-            err = seq_end(st, tmp);
-            if (!err) {
-              g->rep[0] = tmp.rep[0]; g->rep[1] = tmp.rep[1]; g->rep[2] = tmp.rep[2];
-              g->blkOut = tmp.blkOut; g->dstPos = tmp.dstPos;
-            }
-          }
-          if (err) {
-            if (!g->status) g->status = err;
-            g->blkType = BT_NONE;
-            g->flags |= FF_DONE;
-          }
-          active = false;
-        }
+      for (u32 k = 0; k < steps; k += 2) {
+        st.br.refill_point();  // at least every 2 steps (SeqReader)
+        *out++ = seq_step(tLL, tML, tOF, lutLL, lutML, st);
+        if (k + 1 < steps) *out++ = seq_step(tLL, tML, tOF, lutLL, lutML, st);
       }
+    }
+    __syncwarp();
+    if (active && st.i == st.n) {
+      FrameCtx* g = &ctxs[frame];
+      FrameCtx tmp;
+      u32 err = seq_end(st, tmp);
+      if (!err) {
+        g->rep[0] = tmp.rep[0]; g->rep[1] = tmp.rep[1]; g->rep[2] = tmp.rep[2];
+        g->blkOut = tmp.blkOut; g->dstPos = tmp.dstPos;
+      } else {
+        if (!g->status) g->status = err;
+        g->blkType = BT_NONE;
+        g->flags |= FF_DONE;
+      }
+      active = false;
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ u32 warp_incl_scan(u32 v, u32 lane) {
-#pragma unroll
-  for (u32 d = 1; d < 32; d <<= 1) {
-    u32 o = __shfl_up_sync(kFull, v, d);
-    if (lane >= d) v += o;
+// Whole-warp forward copy of n bytes between regions that do not overlap: 16-byte stores to the
+// aligned body of dst, the source words funnel-shifted into place (src and dst may have any
+// alignment). Reads whole aligned words, i.e. up to 3 bytes either side of the source range.
+__device__ __forceinline__ void warp_copy_wide(u8* dst, const u8* src, u32 n, u32 lane) {
+  u32 head = (16u - (u32)(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u;
+  if (head > n) head = n;
+  if (lane < head) dst[lane] = src[lane];
+  dst += head; src += head; n -= head;
+  const u32 vecs = n >> 4;
+  const u32 sh = (u32)(reinterpret_cast<uintptr_t>(src) & 3u) * 8u;
+  const u32* sw = reinterpret_cast<const u32*>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)3);
+  uint4* dv = reinterpret_cast<uint4*>(dst);
+  for (u32 v = lane; v < vecs; v += 32) {
+    const u32* p = sw + 4 * v;
+    u32 a = p[0], b = p[1], c = p[2], d = p[3], e = sh ? p[4] : 0u;
+    uint4 o;
+    o.x = __funnelshift_r(a, b, sh);
+    o.y = __funnelshift_r(b, c, sh);
+    o.z = __funnelshift_r(c, d, sh);
+    o.w = __funnelshift_r(d, e, sh);
+    dv[v] = o;
   }
-  return v;
+  const u32 done = vecs << 4, tail = n & 15u;
+  if (lane < tail) dst[done + lane] = src[done + lane];
 }
 
-// Whole-warp forward copy, byte granular; [dst,dst+n) and [src,src+n) do not overlap.
-__device__ __forceinline__ void warp_copy(u8* dst, const u8* src, u32 n, u32 lane) {
-  for (u32 i = lane; i < n; i += 32) dst[i] = src[i];
-}
-
-// One lane copies n (< kLongCopy) bytes: all loads are issued before the stores so the lane pays
-// one memory round trip instead of n. `period` < n means the match overlaps its own output
-// (offset < length): the source is then the period-long pattern that precedes dst.
+// Lanes copy n (< kLongCopy, possibly 0) bytes each, in lock-step; m is a warp-uniform upper bound
+// of n. Loads of a group are issued before its stores so a lane pays one memory round trip per 8
+// bytes. kReadOnlySrc: the source is never written by this kernel (literal scratch / input).
 template <bool kReadOnlySrc>
-__device__ __forceinline__ u8 ld_byte(const u8* p) {
-  // output bytes are re-read through L1 (coherent within the SM that wrote them, and only this
-  // warp writes this frame): consecutive bytes of a match then cost one L2 sector, not one each
-  return kReadOnlySrc ? __ldg(p) : *p;
-}
-
-template <bool kReadOnlySrc>
-__device__ __forceinline__ void lane_copy_short(u8* dst, const u8* src, u32 n, u32 period) {
-  if (period < n) {  // rare: short self-overlapping match, byte-serial pattern walk
-    u32 j = 0;
-    for (u32 i = 0; i < n; i++) {
-      dst[i] = ld_byte<kReadOnlySrc>(src + j);
-      if (++j == period) j = 0;
-    }
-    return;
-  }
-  // full groups of 8 with immediate offsets, then a predicated tail of at most 7
-  while (n >= 8) {
+__device__ __forceinline__ void lanes_copy(u8* dst, const u8* src, u32 n, u32 m) {
+#pragma unroll 1
+  for (u32 k = 0; k < m; k += 8) {
     u8 b[8];
 #pragma unroll
-    for (u32 k = 0; k < 8; k++) b[k] = ld_byte<kReadOnlySrc>(src + k);
+    for (u32 j = 0; j < 8; j++)
+      if (k + j < n) b[j] = kReadOnlySrc ? __ldg(src + k + j) : src[k + j];
 #pragma unroll
-    for (u32 k = 0; k < 8; k++) dst[k] = b[k];
-    src += 8;
-    dst += 8;
-    n -= 8;
+    for (u32 j = 0; j < 8; j++)
+      if (k + j < n) dst[k + j] = b[j];
   }
-  u8 t[7];
-#pragma unroll
-  for (u32 k = 0; k < 7; k++)
-    if (k < n) t[k] = ld_byte<kReadOnlySrc>(src + k);
-#pragma unroll
-  for (u32 k = 0; k < 7; k++)
-    if (k < n) dst[k] = t[k];
 }
 
-__global__ void __launch_bounds__(256) k_seq_execute(const u8* __restrict__ src, u8* dst, const FrameDesc* __restrict__ descs,
+__device__ __forceinline__ u64 shfl64(u64 v, int srcLane) {
+  u32 lo = __shfl_sync(kFull, (u32)v, srcLane), hi = __shfl_sync(kFull, (u32)(v >> 32), srcLane);
+  return (u64)lo | ((u64)hi << 32);
+}
+__device__ __forceinline__ u64 shfl64_up1(u64 v) {
+  u32 lo = __shfl_up_sync(kFull, (u32)v, 1), hi = __shfl_up_sync(kFull, (u32)(v >> 32), 1);
+  return (u64)lo | ((u64)hi << 32);
+}
+
+// Sequence execution, one warp per frame, 32 sequences per iteration (one per lane). The records
+// are cumulative (decode_core.cuh), so a lane gets its literal source, output position and lengths
+// from its own record and its left neighbour's. Literals never depend on matches; matches are
+// resolved in rounds: everything below the first pending match is final, so that match can always
+// run, and so can every later match whose source lies entirely below it.
+// Reference semantics: ZSTD_execSequence, zstd/decompress/zstd_decompress_block.c:704-793.
+__global__ void __launch_bounds__(256, 4) k_seq_execute(const u8* __restrict__ src, u8* dst, const FrameDesc* __restrict__ descs,
                                                      const FrameCtx* __restrict__ ctxs, const u8* __restrict__ lit, u32 litStride,
                                                      const u64* __restrict__ seqs, u32 seqStride, u32 nFrames) {
   u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -340,7 +354,7 @@ __global__ void __launch_bounds__(256) k_seq_execute(const u8* __restrict__ src,
   const u8* fsrc = src + d.srcOff;
   const u32 blkDst = c.blkDst;
   if (c.blkType == BT_RAW) {
-    for (u32 i = lane; i < c.blkSize; i += 32) frame[blkDst + i] = __ldg(fsrc + c.blkSrc + i);
+    warp_copy_wide(frame + blkDst, fsrc + c.blkSrc, c.blkSize, lane);
     return;
   }
   if (c.blkType == BT_RLE) {
@@ -354,34 +368,37 @@ __global__ void __launch_bounds__(256) k_seq_execute(const u8* __restrict__ src,
   const u8* litp = c.litMode == LIT_HUF ? lit + (u64)warp * litStride : fsrc + c.litSrc;
   const u64* sq = seqs + (u64)warp * seqStride;
   const u32 nbSeq = c.nbSeq;
-  u32 pos = blkDst;  // frame-relative output cursor
-  u32 litPos = 0;
+  u64 carry = 0;  // record of the last sequence of the previous iteration
   for (u32 base = 0; base < nbSeq; base += 32) {
-    u64 s = (base + lane < nbSeq) ? __ldg(sq + base + lane) : 0ull;
-    u32 ll = seq_ll(s), ml = seq_ml(s), off = seq_off(s);
-    u32 sumLL = warp_incl_scan(ll, lane);
-    u32 sumOut = warp_incl_scan(ll + ml, lane);
-    u32 myLit = litPos + sumLL - ll;
-    u32 myDst = pos + sumOut - (ll + ml);
-    // literals: long runs by the whole warp, short ones one lane each
+    u32 idx = base + lane;
+    u64 s = __ldg(sq + (idx < nbSeq ? idx : nbSeq - 1));  // lanes past the end repeat the last record: ll = ml = 0
+    u64 p = shfl64_up1(s);
+    if (lane == 0) p = carry;
+    carry = shfl64(s, 31);
+    const u32 pl = rec_lit_end(p), po = rec_out_end(p);
+    const u32 ll = rec_lit_end(s) - pl;
+    const u32 ml = rec_out_end(s) - po - ll;
+    const u32 off = rec_off(s);
+    const u32 myDst = blkDst + po;
+    // ---- literals: long runs by the whole warp, short ones one lane each
     u32 longLit = __ballot_sync(kFull, ll >= kLongCopy);
     while (longLit) {
       int who = __ffs(longLit) - 1;
       longLit &= longLit - 1;
-      u32 L = __shfl_sync(kFull, ll, who), from = __shfl_sync(kFull, myLit, who), to = __shfl_sync(kFull, myDst, who);
+      u32 L = __shfl_sync(kFull, ll, who), from = __shfl_sync(kFull, pl, who), to = __shfl_sync(kFull, myDst, who);
       if (rle) { for (u32 i = lane; i < L; i += 32) frame[to + i] = rleByte; }
-      else { for (u32 i = lane; i < L; i += 32) frame[to + i] = __ldg(litp + from + i); }
+      else warp_copy_wide(frame + to, litp + from, L, lane);
     }
-    if (ll < kLongCopy) {
-      if (rle) { for (u32 i = 0; i < ll; i++) frame[myDst + i] = rleByte; }
-      else lane_copy_short<true>(frame + myDst, litp + myLit, ll, ll);
+    {
+      const u32 n = ll < kLongCopy ? ll : 0;
+      const u32 m = __reduce_max_sync(kFull, n);
+      if (rle) { for (u32 i = 0; i < n; i++) frame[myDst + i] = rleByte; }
+      else lanes_copy<true>(frame + myDst, litp + pl, n, m);
     }
     __syncwarp();
-    // matches: multi-round resolution. Everything below the first pending match is final, so
-    // that match can always run; later matches run in the same round when their source lies
-    // entirely below it.
-    u32 mpos = myDst + ll;
-    u32 msrc = mpos - off;
+    // ---- matches
+    const u32 mpos = myDst + ll;
+    const u32 msrc = mpos - off;
     bool pending = ml > 0;
     for (;;) {
       u32 mask = __ballot_sync(kFull, pending);
@@ -392,28 +409,42 @@ __global__ void __launch_bounds__(256) k_seq_execute(const u8* __restrict__ src,
       if (fml >= kLongCopy) {
         u32 fs = __shfl_sync(kFull, msrc, first), fo = __shfl_sync(kFull, off, first);
         if (fo >= fml) {
-          warp_copy(frame + hwm, frame + fs, fml, lane);
+          warp_copy_wide(frame + hwm, frame + fs, fml, lane);
+        } else if (fo >= 32) {
+          // overlap further than a warp-width: 32-byte slices in order, each reads only final bytes
+          for (u32 i = 0; i < fml; i += 32) {
+            if (i + lane < fml) frame[hwm + i + lane] = frame[fs + i + lane];
+            __syncwarp();
+          }
         } else {
-          // overlapping match: the period [hwm-fo, hwm) is final, every byte is a lookup into it
+          // short period: the period [hwm-fo, hwm) is final, every byte is a lookup into it
           for (u32 i = lane; i < fml; i += 32) frame[hwm + i] = frame[fs + (i % fo)];
         }
         if ((int)lane == first) pending = false;
       } else {
-        bool ready = pending && ml < kLongCopy && ((int)lane == first || msrc + ml <= hwm);
-        if (ready) {
-          lane_copy_short<false>(frame + mpos, frame + msrc, ml, off);
-          pending = false;
+        const bool ready = pending && ml < kLongCopy && ((int)lane == first || msrc + ml <= hwm);
+        u32 n = ready ? ml : 0;
+        if (ready && off < ml) {  // rare: short self-overlapping match (only the first pending one can be), byte-serial
+          u32 j = 0;
+          for (u32 i = 0; i < ml; i++) {
+            frame[mpos + i] = frame[msrc + j];
+            if (++j == off) j = 0;
+          }
+          n = 0;
         }
+        const u32 m = __reduce_max_sync(kFull, n);
+        lanes_copy<false>(frame + mpos, frame + msrc, n, m);
+        if (ready) pending = false;
       }
       __syncwarp();
     }
-    pos += __shfl_sync(kFull, sumOut, 31);
-    litPos += __shfl_sync(kFull, sumLL, 31);
   }
   // trailing literals
-  u32 rest = c.litSize - litPos;
+  const u32 litPos = rec_lit_end(carry);
+  const u32 pos = blkDst + rec_out_end(carry);
+  const u32 rest = c.litSize - litPos;
   if (rle) { for (u32 i = lane; i < rest; i += 32) frame[pos + i] = rleByte; }
-  else { for (u32 i = lane; i < rest; i += 32) frame[pos + i] = __ldg(litp + litPos + i); }
+  else warp_copy_wide(frame + pos, litp + litPos, rest, lane);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -76,6 +76,7 @@ ZraStatus ZraCudaDecodeFrames(ZraCudaContext* context, const void* dSrc, size_t 
                               void* dDst, uint32_t* frameSizes, uint32_t* failedFrame, void* stream) {
   GpuContext& g = context->gpu;
   if (!g.ok()) return st(ZStdError, 1);
+  if (reinterpret_cast<uintptr_t>(dSrc) & 15u) { g.fail("zra-b200: device source pointer must be 16-byte aligned"); return st(ZStdError, 1); }
   uint32_t maxCap = 0;
   for (uint32_t i = 0; i < count; i++) maxCap = frames[i].dstCapacity > maxCap ? frames[i].dstCapacity : maxCap;
   DecodeResult r = g.decode(dSrc, srcSize, reinterpret_cast<const HostFrame*>(frames), nullptr, 0, count, maxCap, dDst, frameSizes,
@@ -90,6 +91,7 @@ ZraStatus ZraCudaDecompressFrames(ZraCudaContext* context, const void* dArchive,
   if (!g.ok()) return st(ZStdError, 1);
   g.bind();
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (reinterpret_cast<uintptr_t>(dArchive) & 15u) { g.fail("zra-b200: device archive pointer must be 16-byte aligned"); return st(ZStdError, 1); }
   ArchiveInfo info;
   ZraStatus hs = read_info(g, dArchive, archiveSize, &info, s);
   if (hs.zra != Success) return hs;
@@ -108,6 +110,7 @@ ZraStatus ZraCudaDecompressBuffer(ZraCudaContext* context, const void* dArchive,
   if (!g.ok()) return st(ZStdError, 1);
   g.bind();
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (reinterpret_cast<uintptr_t>(dArchive) & 15u) { g.fail("zra-b200: device archive pointer must be 16-byte aligned"); return st(ZStdError, 1); }
   ArchiveInfo info;
   ZraStatus hs = read_info(g, dArchive, archiveSize, &info, s);
   if (hs.zra != Success) return hs;
