@@ -309,20 +309,74 @@ __device__ __forceinline__ void warp_copy_wide(u8* dst, const u8* src, u32 n, u3
   if (lane < tail) dst[done + lane] = src[done + lane];
 }
 
-// Lanes copy n (< kLongCopy, possibly 0) bytes each, in lock-step; m is a warp-uniform upper bound
-// of n. Loads of a group are issued before its stores so a lane pays one memory round trip per 8
-// bytes. kReadOnlySrc: the source is never written by this kernel (literal scratch / input).
-template <bool kReadOnlySrc>
-__device__ __forceinline__ void lanes_copy(u8* dst, const u8* src, u32 n, u32 m) {
+// ---- lock-step short copies --------------------------------------------------------------
+// Every lane copies its own n bytes (possibly 0); m is a warp-uniform upper bound of n. Four bytes
+// per trip, written as predicated PTX (one predicate per byte position, loads before stores,
+// immediate offsets): nvcc turns the equivalent C++ into nested divergent branches.
+#define ZRA_PRED4 "setp.gt.s32 p0, %2, 0;\n\tsetp.gt.s32 p1, %2, 1;\n\tsetp.gt.s32 p2, %2, 2;\n\tsetp.gt.s32 p3, %2, 3;\n\t"
+#define ZRA_COPY4(LD, ST)                                                                               \
+  "{\n\t.reg .pred p0, p1, p2, p3;\n\t.reg .b32 b0, b1, b2, b3;\n\t" ZRA_PRED4                          \
+  "@p0 " LD " b0, [%0];\n\t@p1 " LD " b1, [%0+1];\n\t@p2 " LD " b2, [%0+2];\n\t@p3 " LD " b3, [%0+3];\n\t" \
+  "@p0 " ST " [%1], b0;\n\t@p1 " ST " [%1+1], b1;\n\t@p2 " ST " [%1+2], b2;\n\t@p3 " ST " [%1+3], b3;\n\t}"
+
+// global (read-only data: literal scratch / input) -> global
+__device__ __forceinline__ void lanes_copy_ro(u8* d, const u8* s, u32 n, u32 m) {
+  i32 r = (i32)n;
 #pragma unroll 1
-  for (u32 k = 0; k < m; k += 8) {
-    u8 b[8];
-#pragma unroll
-    for (u32 j = 0; j < 8; j++)
-      if (k + j < n) b[j] = kReadOnlySrc ? __ldg(src + k + j) : src[k + j];
-#pragma unroll
-    for (u32 j = 0; j < 8; j++)
-      if (k + j < n) dst[k + j] = b[j];
+  for (u32 k = 0; k < m; k += 4) {
+    asm volatile(ZRA_COPY4("ld.global.nc.u8", "st.global.u8")::"l"(s), "l"(d), "r"(r) : "memory");
+    s += 4; d += 4; r -= 4;
+  }
+}
+// global (output written earlier by this warp) -> global
+__device__ __forceinline__ void lanes_copy_gg(u8* d, const u8* s, u32 n, u32 m) {
+  i32 r = (i32)n;
+#pragma unroll 1
+  for (u32 k = 0; k < m; k += 4) {
+    asm volatile(ZRA_COPY4("ld.global.u8", "st.global.u8")::"l"(s), "l"(d), "r"(r) : "memory");
+    s += 4; d += 4; r -= 4;
+  }
+}
+// shared -> shared (32-bit shared-window addresses)
+__device__ __forceinline__ void lanes_copy_ss(u32 d, u32 s, u32 n, u32 m) {
+  i32 r = (i32)n;
+#pragma unroll 1
+  for (u32 k = 0; k < m; k += 4) {
+    asm volatile(ZRA_COPY4("ld.shared.u8", "st.shared.u8")::"r"(s), "r"(d), "r"(r) : "memory");
+    s += 4; d += 4; r -= 4;
+  }
+}
+// global -> shared, the source fetched as ALIGNED 32-bit words (one L1 request per 4 bytes instead
+// of four) and funnel-shifted into place. Reads whole words: up to 3 bytes before s and 3 bytes
+// after s+n-1 (the callers' buffers allow that). kNc: read-only source.
+template <bool kNc>
+__device__ __forceinline__ u32 ld_word_if(const u32* w, bool p) {
+  u32 v = 0;
+  if (kNc) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.global.nc.u32 %0, [%1];\n\t}" : "+r"(v) : "l"(w), "r"((u32)p) : "memory");
+  } else {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.global.u32 %0, [%1];\n\t}" : "+r"(v) : "l"(w), "r"((u32)p) : "memory");
+  }
+  return v;
+}
+template <bool kNc>
+__device__ __forceinline__ void lanes_copy_gs(u32 d, const u8* s, u32 n, u32 m) {
+  i32 r = (i32)n;
+  const u32 mis = (u32)(reinterpret_cast<uintptr_t>(s) & 3u);
+  const u32 sh = mis * 8u;
+  const i32 thr = 4 - (i32)mis;  // the next word is needed iff more than `thr` bytes are left
+  const u32* w = reinterpret_cast<const u32*>(reinterpret_cast<uintptr_t>(s) & ~(uintptr_t)3);
+  u32 cur = ld_word_if<kNc>(w, r > 0);
+#pragma unroll 1
+  for (u32 k = 0; k < m; k += 4) {
+    const u32 nxt = ld_word_if<kNc>(w + 1, r > thr);
+    const u32 x = __funnelshift_r(cur, nxt, sh);
+    asm volatile(
+        "{\n\t.reg .pred p0, p1, p2, p3;\n\t.reg .b32 b1, b2, b3;\n\t" ZRA_PRED4
+        "shr.u32 b1, %0, 8;\n\tshr.u32 b2, %0, 16;\n\tshr.u32 b3, %0, 24;\n\t"
+        "@p0 st.shared.u8 [%1], %0;\n\t@p1 st.shared.u8 [%1+1], b1;\n\t@p2 st.shared.u8 [%1+2], b2;\n\t@p3 st.shared.u8 [%1+3], b3;\n\t}"
+        ::"r"(x), "r"(d), "r"(r) : "memory");
+    cur = nxt; w += 1; d += 4; r -= 4;
   }
 }
 
@@ -340,10 +394,23 @@ __device__ __forceinline__ u64 shfl64_up1(u64 v) {
 // from its own record and its left neighbour's. Literals never depend on matches; matches are
 // resolved in rounds: everything below the first pending match is final, so that match can always
 // run, and so can every later match whose source lies entirely below it.
+//
+// The L1 request rate, not the instruction count, bounds a byte-granular LZ copy (profiles/r01b:
+// one request per byte moved), so a group's output is ASSEMBLED IN SHARED MEMORY: each warp owns a
+// 4 KiB tile laid out at the same 16-byte phase as the destination; literals and far match sources
+// are fetched as aligned 32-bit words, near matches copy tile to tile, and the finished group
+// leaves with 16-byte coalesced stores. Groups that contain a long literal run or match (>= 64
+// bytes) or regenerate more than the tile holds take the direct global path instead.
 // Reference semantics: ZSTD_execSequence, zstd/decompress/zstd_decompress_block.c:704-793.
-__global__ void __launch_bounds__(256, 4) k_seq_execute(const u8* __restrict__ src, u8* dst, const FrameDesc* __restrict__ descs,
+constexpr u32 kExecWarps = 8;
+constexpr u32 kTileBytes = 4096;
+constexpr u32 kTileStride = kTileBytes + 32;
+constexpr u32 kShortMax = 64;  // sequences with ll and ml below this go through the tile
+
+__global__ void __launch_bounds__(kExecWarps * 32, 4) k_seq_execute(const u8* __restrict__ src, u8* dst, const FrameDesc* __restrict__ descs,
                                                      const FrameCtx* __restrict__ ctxs, const u8* __restrict__ lit, u32 litStride,
                                                      const u64* __restrict__ seqs, u32 seqStride, u32 nFrames) {
+  __shared__ __align__(16) u8 tiles[kExecWarps][kTileStride];
   u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   u32 lane = threadIdx.x & 31;
   if (warp >= nFrames) return;
@@ -363,24 +430,95 @@ __global__ void __launch_bounds__(256, 4) k_seq_execute(const u8* __restrict__ s
     return;
   }
   // ---- compressed block
+  u8* tile = tiles[threadIdx.x >> 5];
+  const u32 tileS = (u32)__cvta_generic_to_shared(tile);
   const bool rle = c.litMode == LIT_RLE;
   const u8 rleByte = (u8)c.litSrc;
   const u8* litp = c.litMode == LIT_HUF ? lit + (u64)warp * litStride : fsrc + c.litSrc;
   const u64* sq = seqs + (u64)warp * seqStride;
   const u32 nbSeq = c.nbSeq;
+  u8* blk = frame + blkDst;  // block-relative positions (the records' outEnd) index this
   u64 carry = 0;  // record of the last sequence of the previous iteration
   for (u32 base = 0; base < nbSeq; base += 32) {
     u32 idx = base + lane;
     u64 s = __ldg(sq + (idx < nbSeq ? idx : nbSeq - 1));  // lanes past the end repeat the last record: ll = ml = 0
     u64 p = shfl64_up1(s);
     if (lane == 0) p = carry;
+    const u32 S0 = rec_out_end(carry);  // block-relative start of this group's output
     carry = shfl64(s, 31);
+    const u32 S = rec_out_end(carry) - S0;
     const u32 pl = rec_lit_end(p), po = rec_out_end(p);
     const u32 ll = rec_lit_end(s) - pl;
     const u32 ml = rec_out_end(s) - po - ll;
     const u32 off = rec_off(s);
+    const bool viaTile = S <= kTileBytes && !__any_sync(kFull, ll >= kShortMax || ml >= kShortMax);
+    if (viaTile) {
+      // tile byte t <-> block byte S0 - a + t, a = 16-byte phase of the group's first output byte
+      const u32 a = (u32)(reinterpret_cast<uintptr_t>(blk + S0) & 15u);
+      u8* gbase = blk + ((i32)S0 - (i32)a);  // 16-byte aligned; tile byte t is gbase[t]
+      const u32 tl = po - S0 + a;  // tile offset of this lane's literals
+      const u32 tm = tl + ll;      // ... and of its match
+      // ---- literals
+      {
+        const u32 m = __reduce_max_sync(kFull, ll);
+        if (rle) { for (u32 i = 0; i < ll; i++) tile[tl + i] = rleByte; }
+        else lanes_copy_gs<true>(tileS + tl, litp + pl, ll, m);
+      }
+      __syncwarp();
+      // ---- matches: source offset relative to the tile; negative = already in the output buffer
+      const i32 ms = (i32)tm - (i32)off;
+      bool pending = ml > 0;
+      for (;;) {
+        const u32 mask = __ballot_sync(kFull, pending);
+        if (!mask) break;
+        const int first = __ffs(mask) - 1;
+        const i32 hwm = (i32)__shfl_sync(kFull, tm, first);
+        const bool ready = pending && ((int)lane == first || ms + (i32)ml <= hwm);
+        const u32 n = ready ? ml : 0;
+        // part A: bytes whose source is below the tile (final, in the output buffer)
+        const u32 nA = ms < (i32)a ? min(n, (u32)((i32)a - ms)) : 0;
+        const u32 mA = __reduce_max_sync(kFull, nA);
+        if (mA) {
+          const bool selfA = nA && off < nA;  // self-overlap inside the global part: byte-serial
+          if (selfA) {
+            for (u32 i = 0; i < nA; i++) tile[tm + i] = i < off ? gbase[ms + (i32)i] : tile[tm + i - off];
+          }
+          lanes_copy_gs<false>(tileS + tm, gbase + ms, selfA ? 0 : nA, mA);
+        }
+        // part B: the rest comes from the tile itself
+        const u32 nB = n - nA;
+        if (__any_sync(kFull, nB != 0)) {
+          __syncwarp();
+          const bool selfB = nB && off < ml;  // only the first pending match can overlap itself
+          if (selfB) {
+            for (u32 i = nA; i < ml; i++) tile[tm + i] = tile[tm + i - off];
+          }
+          const u32 nBB = selfB ? 0 : nB;
+          const u32 mB = __reduce_max_sync(kFull, nBB);
+          lanes_copy_ss(tileS + tm + nA, tileS + (u32)(ms + (i32)nA), nBB, mB);
+        }
+        if (ready) pending = false;
+        __syncwarp();
+      }
+      // ---- the group leaves: aligned 16-byte stores, bytes at the ragged ends
+      {
+        u8* g = gbase;
+        const u32 end = a + S;
+        for (u32 v = lane; v * 16 < end; v += 32) {
+          const u32 lo = v * 16, hi = lo + 16;
+          if (lo >= a && hi <= end) {
+            *reinterpret_cast<uint4*>(g + lo) = *reinterpret_cast<const uint4*>(tile + lo);
+          } else {
+            const u32 b0 = lo > a ? lo : a, b1 = hi < end ? hi : end;
+            for (u32 i = b0; i < b1; i++) g[i] = tile[i];
+          }
+        }
+      }
+      __syncwarp();
+      continue;
+    }
+    // ---- direct path (long runs / matches): straight to the output buffer
     const u32 myDst = blkDst + po;
-    // ---- literals: long runs by the whole warp, short ones one lane each
     u32 longLit = __ballot_sync(kFull, ll >= kLongCopy);
     while (longLit) {
       int who = __ffs(longLit) - 1;
@@ -393,10 +531,9 @@ __global__ void __launch_bounds__(256, 4) k_seq_execute(const u8* __restrict__ s
       const u32 n = ll < kLongCopy ? ll : 0;
       const u32 m = __reduce_max_sync(kFull, n);
       if (rle) { for (u32 i = 0; i < n; i++) frame[myDst + i] = rleByte; }
-      else lanes_copy<true>(frame + myDst, litp + pl, n, m);
+      else lanes_copy_ro(frame + myDst, litp + pl, n, m);
     }
     __syncwarp();
-    // ---- matches
     const u32 mpos = myDst + ll;
     const u32 msrc = mpos - off;
     bool pending = ml > 0;
@@ -433,7 +570,7 @@ __global__ void __launch_bounds__(256, 4) k_seq_execute(const u8* __restrict__ s
           n = 0;
         }
         const u32 m = __reduce_max_sync(kFull, n);
-        lanes_copy<false>(frame + mpos, frame + msrc, n, m);
+        lanes_copy_gg(frame + mpos, frame + msrc, n, m);
         if (ready) pending = false;
       }
       __syncwarp();
@@ -628,7 +765,7 @@ void launch_decode_rounds(const void* src, void* dst, u32 nFrames, u32 rounds, b
     ZRA_MARK(K_HUF_DECODE);
     k_seq_decode<<<seqCtas, kSeqThreads, kSeqWarpSmem, st>>>(in, descs, ctxs, tabs, seqs, lay.seqStride, work, seqList);
     ZRA_MARK(K_SEQ_DECODE);
-    k_seq_execute<<<div_up((u64)nFrames * 32, 256), 256, 0, st>>>(in, static_cast<u8*>(dst), descs, ctxs, lit, lay.litStride, seqs,
+    k_seq_execute<<<div_up((u64)nFrames * 32, kExecWarps * 32), kExecWarps * 32, 0, st>>>(in, static_cast<u8*>(dst), descs, ctxs, lit, lay.litStride, seqs,
                                                                  lay.seqStride, nFrames);
     ZRA_MARK(K_SEQ_EXECUTE);
   }
