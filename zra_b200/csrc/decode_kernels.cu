@@ -346,37 +346,36 @@ __device__ __forceinline__ void lanes_copy_ss(u32 d, u32 s, u32 n, u32 m) {
     s += 4; d += 4; r -= 4;
   }
 }
-// global -> shared, the source fetched as ALIGNED 32-bit words (one L1 request per 4 bytes instead
-// of four) and funnel-shifted into place. Reads whole words: up to 3 bytes before s and 3 bytes
-// after s+n-1 (the callers' buffers allow that). kNc: read-only source.
-template <bool kNc>
+// generic (global or shared) -> shared, eight bytes per trip; the source is fetched as ALIGNED
+// 32-bit words (one L1 request per 4 bytes instead of four) and funnel-shifted into place. Only
+// words that hold at least one wanted byte are read.
 __device__ __forceinline__ u32 ld_word_if(const u32* w, bool p) {
   u32 v = 0;
-  if (kNc) {
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.global.nc.u32 %0, [%1];\n\t}" : "+r"(v) : "l"(w), "r"((u32)p) : "memory");
-  } else {
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.global.u32 %0, [%1];\n\t}" : "+r"(v) : "l"(w), "r"((u32)p) : "memory");
-  }
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.u32 %0, [%1];\n\t}" : "+r"(v) : "l"(w), "r"((u32)p) : "memory");
   return v;
 }
-template <bool kNc>
-__device__ __forceinline__ void lanes_copy_gs(u32 d, const u8* s, u32 n, u32 m) {
+__device__ __forceinline__ void lanes_copy_xs(u32 d, const u8* s, u32 n, u32 m) {
   i32 r = (i32)n;
   const u32 mis = (u32)(reinterpret_cast<uintptr_t>(s) & 3u);
   const u32 sh = mis * 8u;
-  const i32 thr = 4 - (i32)mis;  // the next word is needed iff more than `thr` bytes are left
+  const i32 thr1 = 4 - (i32)mis, thr2 = 8 - (i32)mis;  // word k+1 / k+2 is needed iff more than thr1 / thr2 bytes are left
   const u32* w = reinterpret_cast<const u32*>(reinterpret_cast<uintptr_t>(s) & ~(uintptr_t)3);
-  u32 cur = ld_word_if<kNc>(w, r > 0);
+  u32 cur = ld_word_if(w, r > 0);
 #pragma unroll 1
-  for (u32 k = 0; k < m; k += 4) {
-    const u32 nxt = ld_word_if<kNc>(w + 1, r > thr);
-    const u32 x = __funnelshift_r(cur, nxt, sh);
+  for (u32 k = 0; k < m; k += 8) {
+    const u32 w1 = ld_word_if(w + 1, r > thr1);
+    const u32 w2 = ld_word_if(w + 2, r > thr2);
+    const u32 x0 = __funnelshift_r(cur, w1, sh), x1 = __funnelshift_r(w1, w2, sh);
     asm volatile(
-        "{\n\t.reg .pred p0, p1, p2, p3;\n\t.reg .b32 b1, b2, b3;\n\t" ZRA_PRED4
+        "{\n\t.reg .pred p0, p1, p2, p3, p4, p5, p6, p7;\n\t.reg .b32 b1, b2, b3, b5, b6, b7;\n\t"
+        "setp.gt.s32 p0, %3, 0;\n\tsetp.gt.s32 p1, %3, 1;\n\tsetp.gt.s32 p2, %3, 2;\n\tsetp.gt.s32 p3, %3, 3;\n\t"
+        "setp.gt.s32 p4, %3, 4;\n\tsetp.gt.s32 p5, %3, 5;\n\tsetp.gt.s32 p6, %3, 6;\n\tsetp.gt.s32 p7, %3, 7;\n\t"
         "shr.u32 b1, %0, 8;\n\tshr.u32 b2, %0, 16;\n\tshr.u32 b3, %0, 24;\n\t"
-        "@p0 st.shared.u8 [%1], %0;\n\t@p1 st.shared.u8 [%1+1], b1;\n\t@p2 st.shared.u8 [%1+2], b2;\n\t@p3 st.shared.u8 [%1+3], b3;\n\t}"
-        ::"r"(x), "r"(d), "r"(r) : "memory");
-    cur = nxt; w += 1; d += 4; r -= 4;
+        "shr.u32 b5, %1, 8;\n\tshr.u32 b6, %1, 16;\n\tshr.u32 b7, %1, 24;\n\t"
+        "@p0 st.shared.u8 [%2], %0;\n\t@p1 st.shared.u8 [%2+1], b1;\n\t@p2 st.shared.u8 [%2+2], b2;\n\t@p3 st.shared.u8 [%2+3], b3;\n\t"
+        "@p4 st.shared.u8 [%2+4], %1;\n\t@p5 st.shared.u8 [%2+5], b5;\n\t@p6 st.shared.u8 [%2+6], b6;\n\t@p7 st.shared.u8 [%2+7], b7;\n\t}"
+        ::"r"(x0), "r"(x1), "r"(d), "r"(r) : "memory");
+    cur = w2; w += 2; d += 8; r -= 8;
   }
 }
 
@@ -439,9 +438,15 @@ __global__ void __launch_bounds__(kExecWarps * 32, 4) k_seq_execute(const u8* __
   const u32 nbSeq = c.nbSeq;
   u8* blk = frame + blkDst;  // block-relative positions (the records' outEnd) index this
   u64 carry = 0;  // record of the last sequence of the previous iteration
+  // lanes past the end repeat the last record (ll = ml = 0); the next group's records are requested a
+  // whole iteration ahead
+  u64 sNext = nbSeq ? __ldg(sq + (lane < nbSeq ? lane : nbSeq - 1)) : 0ull;
   for (u32 base = 0; base < nbSeq; base += 32) {
-    u32 idx = base + lane;
-    u64 s = __ldg(sq + (idx < nbSeq ? idx : nbSeq - 1));  // lanes past the end repeat the last record: ll = ml = 0
+    const u64 s = sNext;
+    {
+      const u32 nidx = base + 32 + lane;
+      if (base + 32 < nbSeq) sNext = __ldg(sq + (nidx < nbSeq ? nidx : nbSeq - 1));
+    }
     u64 p = shfl64_up1(s);
     if (lane == 0) p = carry;
     const u32 S0 = rec_out_end(carry);  // block-relative start of this group's output
@@ -462,10 +467,10 @@ __global__ void __launch_bounds__(kExecWarps * 32, 4) k_seq_execute(const u8* __
       {
         const u32 m = __reduce_max_sync(kFull, ll);
         if (rle) { for (u32 i = 0; i < ll; i++) tile[tl + i] = rleByte; }
-        else lanes_copy_gs<true>(tileS + tl, litp + pl, ll, m);
+        else lanes_copy_xs(tileS + tl, litp + pl, ll, m);
       }
       __syncwarp();
-      // ---- matches: source offset relative to the tile; negative = already in the output buffer
+      // ---- matches: source offset relative to the tile; below `a` = already in the output buffer
       const i32 ms = (i32)tm - (i32)off;
       bool pending = ml > 0;
       for (;;) {
@@ -474,28 +479,20 @@ __global__ void __launch_bounds__(kExecWarps * 32, 4) k_seq_execute(const u8* __
         const int first = __ffs(mask) - 1;
         const i32 hwm = (i32)__shfl_sync(kFull, tm, first);
         const bool ready = pending && ((int)lane == first || ms + (i32)ml <= hwm);
-        const u32 n = ready ? ml : 0;
-        // part A: bytes whose source is below the tile (final, in the output buffer)
-        const u32 nA = ms < (i32)a ? min(n, (u32)((i32)a - ms)) : 0;
-        const u32 mA = __reduce_max_sync(kFull, nA);
-        if (mA) {
-          const bool selfA = nA && off < nA;  // self-overlap inside the global part: byte-serial
-          if (selfA) {
-            for (u32 i = 0; i < nA; i++) tile[tm + i] = i < off ? gbase[ms + (i32)i] : tile[tm + i - off];
+        // one lock-step loop serves every ready lane whose source is entirely in the output buffer
+        // or entirely in the tile (generic addresses); the rare rest is done after it
+        const bool inTile = ms >= (i32)a, inOut = ms + (i32)ml <= (i32)a;
+        const bool plain = ready && off >= ml && (inTile || inOut);
+        const u8* sp = inTile ? tile + ms : gbase + ms;
+        const u32 n = plain ? ml : 0;
+        const u32 m = __reduce_max_sync(kFull, n);
+        lanes_copy_xs(tileS + tm, sp, n, m);
+        if (ready && !plain) {
+          // straddles the tile start and / or overlaps its own output: byte-serial
+          for (u32 i = 0; i < ml; i++) {
+            const i32 t = ms + (i32)i;
+            tile[tm + i] = t < (i32)a ? gbase[t] : tile[t];
           }
-          lanes_copy_gs<false>(tileS + tm, gbase + ms, selfA ? 0 : nA, mA);
-        }
-        // part B: the rest comes from the tile itself
-        const u32 nB = n - nA;
-        if (__any_sync(kFull, nB != 0)) {
-          __syncwarp();
-          const bool selfB = nB && off < ml;  // only the first pending match can overlap itself
-          if (selfB) {
-            for (u32 i = nA; i < ml; i++) tile[tm + i] = tile[tm + i - off];
-          }
-          const u32 nBB = selfB ? 0 : nB;
-          const u32 mB = __reduce_max_sync(kFull, nBB);
-          lanes_copy_ss(tileS + tm + nA, tileS + (u32)(ms + (i32)nA), nBB, mB);
         }
         if (ready) pending = false;
         __syncwarp();
