@@ -41,6 +41,8 @@ def parse_args():
     ap.add_argument("--frame-size", type=int, default=65536)
     ap.add_argument("--level", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ra", action="store_true", help="skip the batched random-access leg")
+    ap.add_argument("--ra-size-mib", type=int, default=1024, help="original bytes of the random-access archive (16 KiB frames)")
     return ap.parse_args()
 
 
@@ -169,6 +171,98 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------- batched random access (BASELINE configs[3] shape)
+def run_ra(args, torch, dist, ctx, rank, world, peak):
+    """4 KiB reads at uniform random offsets into a 16 KiB-frame text archive, one read per frame on average
+    (configs[3]: 1M reads over a 16 GiB / 1M-frame archive; here ra-size-mib per GPU at the same density).
+    Device-resident: archive, offsets and results in HBM. Returns the dict for the JSON line."""
+    fs, rsz = 16384, 4096
+    size = args.ra_size_mib << 20
+    data, archive = build_archive(size, fs, 3, seed=107 + rank)
+    count = size // fs
+    rng = np.random.default_rng(42 + rank)
+    offs = rng.integers(0, size - rsz - 1, count).astype(np.uint64)
+    d_in = torch.zeros(archive.size + 64, dtype=torch.uint8, device="cuda")
+    d_in[: archive.size] = torch.from_numpy(archive).cuda()
+    d_off = torch.from_numpy(offs.view(np.int64)).cuda()
+    d_out = torch.empty(count * rsz, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream()
+
+    def step():
+        return ctx.decompress_ra_batch(d_in.data_ptr(), archive.size, d_off.data_ptr(), count, d_out.data_ptr(), uniform_size=rsz,
+                                       stream=stream.cuda_stream)
+
+    unique = step()
+    got = d_out.cpu().numpy().reshape(count, rsz)
+    for i in rng.integers(0, count, 200):
+        assert np.array_equal(got[i], data[int(offs[i]): int(offs[i]) + rsz]), "random-access result differs from the original"
+    step()
+    steps = max(3, min(args.steps, 10))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    # end to end: offsets from pinned host memory, results back to pinned host memory, every step
+    h_off = torch.from_numpy(offs.view(np.int64)).pin_memory()
+    h_out = torch.empty(count * rsz, dtype=torch.uint8).pin_memory()
+    def e2e_step():
+        d_off.copy_(h_off, non_blocking=True)
+        step()
+        h_out.copy_(d_out, non_blocking=True)
+        torch.cuda.synchronize()
+    e2e_step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        e2e_step()
+    dt = (time.perf_counter() - t0) / steps
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    # algorithmic bytes (SURVEY.md 8d): compressed bytes of the unique frames touched + bytes delivered
+    comp = archive.size * (unique / (size // fs))
+    alg = comp + count * rsz
+    out = {"metric": "random 4 KiB reads/s", "value": round(world * count / (ms / 1e3), 1), "unit": "reads/s", "ms_per_step": round(ms, 4),
+           "reads_per_step": world * count, "unique_frames_per_step": world * int(unique),
+           "config": {"workload": f"batched DecompressRA, {count} uniform random 4 KiB reads per GPU into a {args.ra_size_mib} MiB "
+                                  "Zipf-text archive, 16384 B frames, level 3 (configs[3] density: one read per frame)"},
+           "e2e": {"value": round(world * count / dt, 1), "unit": "reads/s", "h2d_bytes_per_step": int(offs.nbytes),
+                   "d2h_bytes_per_step": int(count * rsz)},
+           "roofline": {"bound": "hbm", "achieved": round(alg / (ms / 1e3) / 1e9, 2), "peak": peak, "unit": "GB/s",
+                        "frac": round(alg / (ms / 1e3) / 1e9 / peak, 5), "algorithmic_bytes_per_step": int(alg)}}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            import ctypes as C
+
+            import refzra
+
+            L = refzra.ref()
+            threads = os.cpu_count() or 1
+            sample = min(count, 32768)
+            o = np.ascontiguousarray(offs[:sample])
+            res = np.zeros(sample * rsz, np.uint8)
+            st = (C.c_int * 2)()
+            t0 = time.perf_counter()
+            rc = L.ref_ra_mt(refzra._p(archive), archive.size, o.ctypes.data_as(C.POINTER(C.c_uint64)), sample, rsz, refzra._p(res), threads, st)
+            dtc = time.perf_counter() - t0
+            assert rc == 0 and np.array_equal(res.reshape(sample, rsz)[5], data[int(o[5]): int(o[5]) + rsz])
+            out["cpu_baseline"] = {"value": round(sample / dtc, 1), "unit": "reads/s", "cores": threads, "kind": "reference",
+                                   "sample": f"the first {sample} reads, {threads} host threads each with its own zra::Decompressor"}
+        except Exception as e:
+            out["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
+    del d_in, d_out
+    return out
+
+
 # ---------------------------------------------------------------- GPU arm
 def run_gpu(args):
     import torch
@@ -273,6 +367,12 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * size * e2e_steps / float(t.item()) / 1e9
 
+    ra = None
+    if not args.no_ra:
+        del d_ref
+        torch.cuda.empty_cache()
+        ra = run_ra(args, torch, dist, ctx, rank, world, peak)
+
     if rank == 0:
         line = {
             "metric": "decompress GB/s", "value": round(value, 3), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
@@ -289,6 +389,8 @@ def run_gpu(args):
             "gpu_launches": int(launches),
             "roofline": roofline,
         }
+        if ra is not None:
+            line["random_access"] = ra
         if world == 1 and not args.no_cpu_baseline:
             try:
                 threads = os.cpu_count() or 1

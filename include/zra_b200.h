@@ -72,6 +72,23 @@ ZRA_EXPORT ZraStatus ZraCudaDecompressFrames(ZraCudaContext* context, const void
                                              uint64_t firstFrame, uint64_t frameCount, void* dOutput, size_t outputCapacity,
                                              void* stream);
 
+/* Batched random access (north_star item 4): `count` reads against one device-resident archive in a
+ * single call. The reference serves one read per call — zra::DecompressRA (source/zra.cpp:258-296) /
+ * zra::Decompressor::Decompress (source/zra.cpp:369-413): frame index = offset / frameSize, seek-table
+ * lookup, decode of every touched frame, copy of the slice. Here the requests are mapped to frame
+ * indices on the device, frames are DE-DUPLICATED across the batch (each is decoded once), and the
+ * requested slices are gathered. All three request arrays are DEVICE pointers:
+ *   dOffsets[i]     uncompressed offset of read i
+ *   dSizes[i]       its size; NULL = every read is `uniformSize` bytes
+ *   dOutOffsets[i]  where its bytes go inside dOutput; NULL = i * uniformSize (needs dSizes == NULL)
+ * maxSize bounds every size (ignored when dSizes == NULL). Bounds follow Decompressor::Decompress:
+ * offset + size > uncompressedSize is OutOfBoundsAccess and *badRequest (may be NULL) is its index.
+ * *uniqueFrames (may be NULL) receives the number of frames actually decoded. */
+ZRA_EXPORT ZraStatus ZraCudaDecompressRABatch(ZraCudaContext* context, const void* dArchive, size_t archiveSize,
+                                              const uint64_t* dOffsets, const uint32_t* dSizes, const uint64_t* dOutOffsets,
+                                              uint32_t uniformSize, uint32_t maxSize, uint64_t count, void* dOutput,
+                                              uint64_t* uniqueFrames, uint64_t* badRequest, void* stream);
+
 /* zra::CompressBuffer (source/zra.cpp:194-234) with input and archive resident in HBM: every frame
  * is compressed by the GPU encoder (zstd levels 1-3 semantics; level 0 = 3, higher levels use the
  * strongest implemented parser), the 40-bit seek table is the device prefix scan of the frame sizes

@@ -111,6 +111,60 @@ def test_random_access_in_memory(name):
     assert e.value.code == zra_b200.StatusCode.OutOfBoundsAccess
 
 
+@pytest.mark.parametrize("name", ["text_f16384_l3", "text_f262144_l3", "text_f1000_l5", "mixed_f16384_l3"])
+def test_random_access_batch(torch_cuda, ctx, name):
+    """ZraCudaDecompressRABatch: every read equals the oracle's DecompressRA / a slice of the full output; frames are
+    de-duplicated across the batch."""
+    torch = torch_cuda
+    archive, meta = golden_archive(name)
+    full = refzra.oracle_decompress_buffer(archive)
+    n, fs = meta["bytes"], meta["frameSize"]
+    d_in = to_device(torch, archive)
+    rng = np.random.default_rng(5)
+    # uniform 4 KiB reads (the BASELINE shape), heavy frame sharing
+    size = min(4096, n // 2)
+    offs = np.concatenate([rng.integers(0, n - size + 1, 700), [0, n - size, fs - 1, max(0, fs - size)]]).astype(np.uint64)
+    d_off = torch.from_numpy(offs.view(np.int64)).cuda()
+    d_out = torch.full((offs.size * size,), 0xAA, dtype=torch.uint8, device="cuda")
+    unique = ctx.decompress_ra_batch(d_in.data_ptr(), archive.size, d_off.data_ptr(), offs.size, d_out.data_ptr(), uniform_size=size)
+    got = d_out.cpu().numpy().reshape(offs.size, size)
+    touched = set()
+    for i, o in enumerate(offs):
+        o = int(o)
+        assert np.array_equal(got[i], full[o: o + size]), (i, o)
+        touched.update(range(o // fs, (o + size - 1) // fs + 1))
+    assert unique == len(touched)
+    for i in (0, 5, 11):  # against the oracle's restatement of the reference's streaming random access
+        assert np.array_equal(got[i], refzra.oracle_decompress_ra(archive, int(offs[i]), size, in_memory_quirk=False))
+    # a second batch on the same context (the frame->slot map must have been reset)
+    unique2 = ctx.decompress_ra_batch(d_in.data_ptr(), archive.size, d_off.data_ptr(), 10, d_out.data_ptr(), uniform_size=size)
+    assert unique2 == len({f for o in offs[:10] for f in range(int(o) // fs, (int(o) + size - 1) // fs + 1)})
+    # ragged reads with explicit output offsets, including empty reads and the very last byte
+    sizes = rng.integers(0, min(3 * fs, n), 200).astype(np.uint32)
+    roffs = np.array([rng.integers(0, n - int(s) + 1) for s in sizes], dtype=np.uint64)
+    sizes[0], roffs[0] = 1, n - 1
+    outo = np.concatenate([[0], np.cumsum(sizes.astype(np.uint64))[:-1]]).astype(np.uint64)
+    total = int(sizes.sum())
+    d_o = torch.from_numpy(roffs.view(np.int64)).cuda()
+    d_s = torch.from_numpy(sizes.view(np.int32)).cuda()
+    d_oo = torch.from_numpy(outo.view(np.int64)).cuda()
+    d_out2 = torch.zeros(total + 16, dtype=torch.uint8, device="cuda")
+    ctx.decompress_ra_batch(d_in.data_ptr(), archive.size, d_o.data_ptr(), sizes.size, d_out2.data_ptr(), d_sizes=d_s.data_ptr(),
+                            d_out_offsets=d_oo.data_ptr(), max_size=int(sizes.max()))
+    got2 = d_out2.cpu().numpy()
+    for o, s, w in zip(roffs, sizes, outo):
+        assert np.array_equal(got2[int(w): int(w) + int(s)], full[int(o): int(o) + int(s)])
+    # bounds: offset + size > uncompressedSize is OutOfBoundsAccess (zra::Decompressor::Decompress), with the request index
+    bad = offs.copy()
+    bad[7] = n - size + 1
+    d_bad = torch.from_numpy(bad.view(np.int64)).cuda()
+    with pytest.raises(zra_b200.ZraError) as e:
+        ctx.decompress_ra_batch(d_in.data_ptr(), archive.size, d_bad.data_ptr(), bad.size, d_out.data_ptr(), uniform_size=size)
+    assert e.value.code == zra_b200.StatusCode.OutOfBoundsAccess and e.value.bad_request == 7
+    # ... and the context still works afterwards
+    assert ctx.decompress_ra_batch(d_in.data_ptr(), archive.size, d_off.data_ptr(), 10, d_out.data_ptr(), uniform_size=size) == unique2
+
+
 def test_streaming_decompressor_and_full_decompressor():
     archive, meta = golden_archive("text_f16384_l3")
     full = refzra.oracle_decompress_buffer(archive)

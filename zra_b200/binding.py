@@ -104,6 +104,7 @@ def lib():
         "ZraCudaDecompressBuffer": (ZraStatus, [vp, vp, sz, vp, sz, vp]),
         "ZraCudaDecompressFrames": (ZraStatus, [vp, vp, sz, u64, u64, vp, sz, vp]),
         "ZraCudaCompressBuffer": (ZraStatus, [vp, vp, sz, vp, sz, P(sz), C.c_int8, u32, C.c_bool, vp, sz, vp]),
+        "ZraCudaDecompressRABatch": (ZraStatus, [vp, vp, sz, vp, vp, vp, u32, u32, u64, vp, P(u64), P(u64), vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -343,6 +344,20 @@ class CudaContext:
     def decompress_frames(self, d_archive, archive_size, first_frame, frame_count, d_out, out_capacity, stream=0):
         self._raise(lib().ZraCudaDecompressFrames(self._c, C.c_void_p(d_archive), archive_size, first_frame, frame_count,
                                                   C.c_void_p(d_out), out_capacity, C.c_void_p(stream)))
+
+    def decompress_ra_batch(self, d_archive, archive_size, d_offsets, count, d_out, uniform_size=0, d_sizes=0, d_out_offsets=0,
+                            max_size=0, stream=0):
+        """Batched random access; all request arrays are device pointers (0 = absent). Returns the number of
+        frames decoded after de-duplication."""
+        unique, bad = C.c_uint64(0), C.c_uint64(0)
+        st = lib().ZraCudaDecompressRABatch(self._c, C.c_void_p(d_archive), archive_size, C.c_void_p(d_offsets),
+                                            C.c_void_p(d_sizes or None), C.c_void_p(d_out_offsets or None), uniform_size, max_size,
+                                            count, C.c_void_p(d_out), C.byref(unique), C.byref(bad), C.c_void_p(stream))
+        if st.zra != 0:
+            e = ZraError(st.zra, st.zstd, (lib().ZraGetErrorString(st) or b"").decode() + f" | request {bad.value} | " + self.last_error())
+            e.bad_request = bad.value
+            raise e
+        return unique.value
 
     def compress_buffer(self, d_in, in_size, d_out, out_capacity, level=0, frame_size=16384, checksum=True, meta=b"", stream=0):
         """Device-resident CompressBuffer; returns the archive size."""

@@ -34,7 +34,8 @@ GpuContext::GpuContext(int device) {
 GpuContext::~GpuContext() {
   if (!ok_) return;
   cudaSetDevice(device_);
-  for (DevBuf* b : {&scratch, &stageIn, &stageOut, &misc})
+  if (raHost_) cudaFreeHost(raHost_);
+  for (DevBuf* b : {&scratch, &stageIn, &stageOut, &misc, &raSlotOf, &raUnique, &raDescs, &raFrames})
     if (b->p) cudaFree(b->p);
   for (auto& s : pool_)
     if (s) cudaStreamDestroy(s);
@@ -180,7 +181,8 @@ DecodeResult GpuContext::decode(const void* dSrc, size_t srcSize, const HostFram
                                                cudaMemcpyHostToDevice, c.st), "source upload"))
             return fail_cuda();
         }
-        if (check(cudaMemcpyAsync(c.scratch + c.lay.offDescs, frames + c.f0, sizeof(HostFrame) * (size_t)c.n, cudaMemcpyHostToDevice,
+        // `frames` may also be a DEVICE array (batched random access builds its descriptors on the GPU)
+        if (check(cudaMemcpyAsync(c.scratch + c.lay.offDescs, frames + c.f0, sizeof(HostFrame) * (size_t)c.n, cudaMemcpyDefault,
                                   c.st), "descriptor upload"))
           return fail_cuda();
       } else {

@@ -10,6 +10,7 @@
 #include <string>
 
 #include "decode_launch.h"
+#include "ra_launch.h"
 
 namespace zrab {
 
@@ -65,6 +66,7 @@ class GpuContext {
   // Grow-only device buffers.
   void* ensure(DevBuf& b, size_t bytes);
   DevBuf scratch, stageIn, stageOut, misc;
+  DevBuf raSlotOf, raUnique, raDescs, raFrames;  // batched random access (ra_context.cu)
 
   // Decodes frames described either by a host array (`frames`) or, when frames == nullptr, by the
   // seek table of a device-resident archive (`info`, firstFrame, dstBase). Synchronous.
@@ -74,6 +76,18 @@ class GpuContext {
   DecodeResult decode(const void* dSrc, size_t srcSize, const HostFrame* frames, const ArchiveInfo* info, uint64_t firstFrame,
                       uint64_t nFrames, uint32_t maxDstCap, void* dDst, uint32_t* frameSizes, cudaStream_t st,
                       const HostStaging* io = nullptr);
+
+  // Batched random access over a device-resident archive: every frame a
+  // batch touches is decoded once, the requested slices are gathered into dOut. All arrays of `b`
+  // are device pointers; maxSize bounds every request's size. Synchronous.
+  struct RaResult {
+    bool cudaFailed{false};
+    int zra{0}, zstd{0};          // zra::StatusCode / ZSTD_ErrorCode
+    uint64_t badRequest{~0ull};   // first request that is out of bounds (zra == 5)
+    uint64_t uniqueFrames{0};     // frames decoded (after de-duplication, summed over sub-batches)
+  };
+  RaResult random_access(const void* dArchive, size_t archiveSize, const ArchiveInfo& info, RaBatch b, uint64_t count,
+                         uint32_t maxSize, void* dOut, cudaStream_t st);
 
   // Compression results.
   struct CompressStatus {
@@ -107,6 +121,8 @@ class GpuContext {
   cudaStream_t pool_[kPoolStreams] = {};
   cudaEvent_t forkEvent_{nullptr};
   uint32_t* summaryHost_{nullptr};  // pinned, 4 words per chunk
+  uint32_t* raHost_{nullptr};       // pinned, {unique frames, first bad request}
+  uint64_t raSlotFrames_{0};        // entries of raSlotOf that are initialised to "empty"
   static constexpr uint32_t kMaxChunks = 1024;
 };
 

@@ -120,6 +120,31 @@ ZraStatus ZraCudaDecompressBuffer(ZraCudaContext* context, const void* dArchive,
   return from(g.decode(dArchive, archiveSize, nullptr, &info, 0, info.frames, maxCap, dOutput, nullptr, s));
 }
 
+ZraStatus ZraCudaDecompressRABatch(ZraCudaContext* context, const void* dArchive, size_t archiveSize, const uint64_t* dOffsets,
+                                   const uint32_t* dSizes, const uint64_t* dOutOffsets, uint32_t uniformSize, uint32_t maxSize,
+                                   uint64_t count, void* dOutput, uint64_t* uniqueFrames, uint64_t* badRequest, void* stream) {
+  GpuContext& g = context->gpu;
+  if (!g.ok()) return st(ZStdError, 1);
+  g.bind();
+  if (uniqueFrames) *uniqueFrames = 0;
+  if (badRequest) *badRequest = ~0ull;
+  if (!dSizes) maxSize = uniformSize;
+  if (dSizes && !dOutOffsets) { g.fail("zra-b200: per-request sizes need per-request output offsets"); return st(ZStdError, 42); }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (reinterpret_cast<uintptr_t>(dArchive) & 15u) { g.fail("zra-b200: device archive pointer must be 16-byte aligned"); return st(ZStdError, 1); }
+  ArchiveInfo info;
+  ZraStatus hs = read_info(g, dArchive, archiveSize, &info, s);
+  if (hs.zra != Success) return hs;
+  RaBatch b{};
+  b.offsets = dOffsets; b.sizes = dSizes; b.outOffsets = dOutOffsets; b.uniformSize = uniformSize;
+  GpuContext::RaResult r = g.random_access(dArchive, archiveSize, info, b, count, maxSize, dOutput, s);
+  if (uniqueFrames) *uniqueFrames = r.uniqueFrames;
+  if (badRequest) *badRequest = r.badRequest;
+  if (r.cudaFailed) return st(ZStdError, 1);
+  if (r.zra) return st(static_cast<ZraStatusCode>(r.zra), r.zstd);
+  return st(Success);
+}
+
 ZraStatus ZraCudaCompressBuffer(ZraCudaContext* context, const void* dInput, size_t inputSize, void* dOutput, size_t outputCapacity,
                                 size_t* outputSize, int8_t compressionLevel, uint32_t frameSize, bool checksum, const void* metaBuffer,
                                 size_t metaSize, void* stream) {
