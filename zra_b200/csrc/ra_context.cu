@@ -31,9 +31,12 @@ GpuContext::RaResult GpuContext::random_access(const void* dArchive, size_t arch
   DecodeLayout one;
   const uint32_t cap = (uint32_t)std::min<uint64_t>(info.frameSize, info.uncompressedSize);
   const size_t perFrame = decode_scratch_bytes(1, cap, &one) + info.frameSize + 64;
-  const uint64_t budget = 6ull << 30;
-  const uint64_t maxFrames = std::max<uint64_t>(touch, std::min<uint64_t>(budget / perFrame, info.frames + touch));
-  const uint64_t perBatch = std::min<uint64_t>(std::max<uint64_t>(1, maxFrames / touch), 1u << 30);
+  const uint64_t budget = 16ull << 30;
+  const uint64_t budgetFrames = std::max<uint64_t>(touch, budget / perFrame);
+  // a batch can never touch more than every frame of the archive: if those fit, the whole batch is one
+  // sub-batch (frames are then decoded exactly once); otherwise bound the frames a sub-batch can touch
+  const uint64_t perBatch = info.frames <= budgetFrames ? std::min<uint64_t>(count, 1u << 30)
+                                                        : std::min<uint64_t>(std::max<uint64_t>(1, budgetFrames / touch), 1u << 30);
   uint32_t* slotOf = static_cast<uint32_t*>(raSlotOf.p);
   for (uint64_t r0 = 0; r0 < count; r0 += perBatch) {
     const uint32_t n = (uint32_t)std::min<uint64_t>(perBatch, count - r0);
