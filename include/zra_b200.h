@@ -100,6 +100,32 @@ ZRA_EXPORT ZraStatus ZraCudaCompressBuffer(ZraCudaContext* context, const void* 
                                            size_t outputCapacity, size_t* outputSize, int8_t compressionLevel, uint32_t frameSize,
                                            bool checksum, const void* metaBuffer, size_t metaSize, void* stream);
 
+/* ---- sharding across GPUs ---------------------------------------------------------
+ * Frames are independent, so GPU g of G owns the contiguous frame range [g*F/G, (g+1)*F/G).
+ * Decompression of a shard is ZraCudaDecompressFrames above (no exchange). Compression of a shard is
+ * ZraCudaCompressFrames: the shard's frames back to back plus their sizes; the ONE exchange step is
+ * the gather of the per-frame sizes (equivalently: the exclusive scan of the per-shard totals gives
+ * every shard its base offset), after which ZraShardBuildHeader serialises the archive header. */
+
+/* zra::Compressor::Compress (source/zra.cpp:319-350) for a device-resident shard: dInput[0, inputSize)
+ * is cut into frameSize frames (only the last may be short), each becomes one zstd frame, written
+ * back to back at dOutput. frameSizes (HOST array, ceil(inputSize / frameSize) entries) receives the
+ * compressed size of every frame, *outputSize the total. outputCapacity >= ZSTD_compressBound(frameSize)
+ * * frames is always enough. The input must be readable up to 8 bytes past inputSize. */
+ZRA_EXPORT ZraStatus ZraCudaCompressFrames(ZraCudaContext* context, const void* dInput, size_t inputSize, uint32_t frameSize,
+                                           int8_t compressionLevel, bool checksum, void* dOutput, size_t outputCapacity,
+                                           uint64_t* frameSizes, size_t* outputSize, void* stream);
+
+/* Bytes of the header of an archive with `frames` frames and metaSize bytes of metadata. Host only. */
+ZRA_EXPORT size_t ZraShardHeaderSize(uint64_t frames, size_t metaSize);
+
+/* Serialises FixedHeader + meta + 40-bit seek table + CRC-32 (source/zra.cpp:111-134, 201-231) from the
+ * compressed size of every frame in archive order (the exclusive scan into offsets happens here).
+ * Host only, needs no GPU. Fails with CompressedSizeTooLarge when the total reaches 2^40 and with
+ * OutputBufferTooSmall when outCapacity < ZraShardHeaderSize(frames, metaSize). */
+ZRA_EXPORT ZraStatus ZraShardBuildHeader(uint64_t uncompressedSize, uint32_t frameSize, const void* metaBuffer, size_t metaSize,
+                                         const uint64_t* frameSizes, uint64_t frames, void* out, size_t outCapacity);
+
 #ifdef __cplusplus
 }
 #endif

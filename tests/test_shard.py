@@ -1,0 +1,104 @@
+"""Multi-GPU sharding logic on CPU: world_size-2 and -3 gloo process groups.
+
+The exchange step of sharded compression — all-gather of the per-frame compressed sizes / exclusive
+scan of the per-shard totals — and the header stitching (ZraShardBuildHeader, host-only C-ABI) are
+checked against an archive the unmodified reference wrote in one piece: frames are independent
+(SURVEY.md E11 [probed]), so the stitched archive must be byte-identical."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+import refzra
+from zra_b200 import shard, synth
+
+needs_ref = pytest.mark.skipif(not refzra.have_ref(), reason="oracle/_ref not present")
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n, fs, level, q):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        data = synth.text(n, seed=5, threads=1)
+        frames = (n + fs - 1) // fs
+        lo, hi = shard.byte_range(n, fs, rank, world)
+        f0, f1 = shard.frame_range(frames, rank, world)
+        # this rank's frames, made by the reference (the CPU tier has no GPU encoder): a shard-local archive
+        local = refzra.ref_compress(data[lo:hi], level, fs, True) if hi > lo else None
+        if local is not None:
+            hdr = 38 + 5 * (f1 - f0 + 1)
+            t = local[38:hdr].reshape(-1, 5).astype(np.uint64)
+            offs = t[:, 0] | (t[:, 1] << 8) | (t[:, 2] << 16) | (t[:, 3] << 24) | (t[:, 4] << 32)
+            sizes, payload = np.diff(offs), local[hdr:]
+        else:
+            sizes, payload = np.zeros(0, np.uint64), np.zeros(0, np.uint8)
+        all_sizes, base, total = shard.exchange_frame_sizes(sizes, frames)
+        header = shard.build_header(n, fs, all_sizes)
+        q.put((rank, base, total, header.tobytes(), payload.tobytes()))
+    finally:
+        dist.destroy_process_group()
+
+
+@needs_ref
+@pytest.mark.parametrize("world,n,fs", [(2, 1 << 20, 16384), (3, (1 << 20) + 777, 65536), (2, 40000, 16384)])
+def test_sharded_compress_stitches_to_the_reference_archive(world, n, fs):
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, fs, 3, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    whole = refzra.ref_compress(synth.text(n, seed=5, threads=1), 3, fs, True)
+    header = results[0][3]
+    assert all(r[3] == header for r in results)  # every rank stitched the same header
+    total = results[0][2]
+    body = bytearray(total)
+    for rank, base, tot, _, payload in results:
+        assert tot == total
+        body[base: base + len(payload)] = payload  # the final gather: shard bytes at their scanned base offsets
+    assert header + bytes(body) == whole.tobytes()
+
+
+def test_frame_ranges_partition_the_archive():
+    for frames in (0, 1, 7, 8, 1000, 16385):
+        for world in (1, 2, 3, 8):
+            rs = [shard.frame_range(frames, r, world) for r in range(world)]
+            assert rs[0][0] == 0 and rs[-1][1] == frames
+            assert all(a[1] == b[0] for a, b in zip(rs, rs[1:]))
+            assert max(b - a for a, b in rs) - min(b - a for a, b in rs) <= 1
+
+
+def test_build_header_matches_the_oracle():
+    rng = np.random.default_rng(0)
+    for frames, fs, meta in ((1, 16384, b""), (5, 1000, b"meta!"), (300, 65536, b"")):
+        sizes = rng.integers(9, 70000, frames).astype(np.uint64)
+        n = (frames - 1) * fs + 17
+        got = shard.build_header(n, fs, sizes, meta)
+        offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+        import ctypes as C
+
+        o = refzra.oracle()
+        out = np.zeros(38 + len(meta) + 5 * (frames + 1), np.uint8)
+        m = np.frombuffer(meta, np.uint8)
+        o.zra_oracle_build_header(out.ctypes.data_as(C.c_void_p), n, fs, m.ctypes.data_as(C.c_void_p) if m.size else None, m.size,
+                                  offs.ctypes.data_as(C.POINTER(C.c_uint64)), frames + 1)
+        assert np.array_equal(got, out)

@@ -104,6 +104,9 @@ def lib():
         "ZraCudaDecompressBuffer": (ZraStatus, [vp, vp, sz, vp, sz, vp]),
         "ZraCudaDecompressFrames": (ZraStatus, [vp, vp, sz, u64, u64, vp, sz, vp]),
         "ZraCudaCompressBuffer": (ZraStatus, [vp, vp, sz, vp, sz, P(sz), C.c_int8, u32, C.c_bool, vp, sz, vp]),
+        "ZraCudaCompressFrames": (ZraStatus, [vp, vp, sz, u32, C.c_int8, C.c_bool, vp, sz, P(u64), P(sz), vp]),
+        "ZraShardHeaderSize": (sz, [u64, sz]),
+        "ZraShardBuildHeader": (ZraStatus, [u64, u32, vp, sz, P(u64), u64, vp, sz]),
         "ZraCudaDecompressRABatch": (ZraStatus, [vp, vp, sz, vp, vp, vp, u32, u32, u64, vp, P(u64), P(u64), vp]),
     }
     for name, (res, args) in sig.items():

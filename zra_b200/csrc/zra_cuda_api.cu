@@ -163,4 +163,41 @@ ZraStatus ZraCudaCompressBuffer(ZraCudaContext* context, const void* dInput, siz
   return st(Success);
 }
 
+ZraStatus ZraCudaCompressFrames(ZraCudaContext* context, const void* dInput, size_t inputSize, uint32_t frameSize,
+                                int8_t compressionLevel, bool checksum, void* dOutput, size_t outputCapacity, uint64_t* frameSizes,
+                                size_t* outputSize, void* stream) {
+  GpuContext& g = context->gpu;
+  if (!g.ok()) return st(ZStdError, 1);
+  if (!frameSize) return st(ZStdError, 42);  // parameter_outOfBound
+  *outputSize = 0;
+  GpuContext::CompressStatus r = g.compress_frames(dInput, inputSize, frameSize, compressionLevel, checksum, dOutput, outputCapacity,
+                                                   frameSizes, static_cast<cudaStream_t>(stream));
+  if (r.cudaFailed) return st(ZStdError, 1);
+  if (r.zra) return st(static_cast<ZraStatusCode>(r.zra));
+  *outputSize = r.total;
+  return st(Success);
+}
+
+size_t ZraShardHeaderSize(uint64_t frames, size_t metaSize) { return kFixedHeaderSize + metaSize + kEntrySize * (size_t)(frames + 1); }
+
+ZraStatus ZraShardBuildHeader(uint64_t uncompressedSize, uint32_t frameSize, const void* metaBuffer, size_t metaSize,
+                              const uint64_t* frameSizes, uint64_t frames, void* out, size_t outCapacity) {
+  const size_t total = ZraShardHeaderSize(frames, metaSize);
+  if (outCapacity < total) return st(OutputBufferTooSmall);
+  if (!frameSize || frames + 1 != table_entries(uncompressedSize, frameSize)) return st(InputFrameSizeMismatch);
+  uint8_t* p = static_cast<uint8_t*>(out);
+  write_fixed_header(p, uncompressedSize, (uint32_t)(frames + 1), frameSize, (uint32_t)metaSize);
+  if (metaSize) memcpy(p + kFixedHeaderSize, metaBuffer, metaSize);
+  uint8_t* table = p + kFixedHeaderSize + metaSize;
+  uint64_t offset = 0;
+  for (uint64_t f = 0; f < frames; f++) {
+    put_le(table + kEntrySize * f, offset, 5);
+    offset += frameSizes[f];
+    if (offset >= kMaxCompressedSize) return st(CompressedSizeTooLarge);
+  }
+  put_le(table + kEntrySize * frames, offset, 5);
+  put_le(p + 14, header_hash_host(p, total), 4);
+  return st(Success);
+}
+
 }  // extern "C"

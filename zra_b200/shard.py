@@ -1,0 +1,81 @@
+"""Sharding of one ZRA archive across the GPUs of a box — host-side orchestration.
+
+Frames are independent, so rank r of W owns the contiguous frame range frame_range(F, r, W):
+  * decompression: no exchange at all — every rank decodes its range straight from the seek table
+    (ZraCudaDecompressFrames); an optional all-gather (NCCL over NVLink) assembles the output;
+  * compression: every rank compresses its range (ZraCudaCompressFrames), then ONE exchange step:
+    the per-frame compressed sizes are all-gathered (equivalently an exclusive scan of the per-shard
+    totals gives every shard its base offset) and the header is stitched (ZraShardBuildHeader).
+One process per GPU, torch.distributed for the plumbing (backend nccl on GPUs, gloo in the CPU tests).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import binding
+
+
+def frame_range(frames, rank, world):
+    """Contiguous, balanced: [frames*rank//world, frames*(rank+1)//world)."""
+    return frames * rank // world, frames * (rank + 1) // world
+
+
+def byte_range(uncompressed_size, frame_size, rank, world):
+    """Uncompressed byte range of the rank's frames."""
+    frames = (uncompressed_size + frame_size - 1) // frame_size
+    f0, f1 = frame_range(frames, rank, world)
+    return min(f0 * frame_size, uncompressed_size), min(f1 * frame_size, uncompressed_size)
+
+
+def shard_header_size(frames, meta_size=0):
+    return binding.lib().ZraShardHeaderSize(frames, meta_size)
+
+
+def build_header(uncompressed_size, frame_size, frame_sizes, meta=b""):
+    """Archive header from the compressed size of every frame (host only, no GPU)."""
+    L = binding.lib()
+    sizes = np.ascontiguousarray(frame_sizes, dtype=np.uint64)
+    m = np.frombuffer(bytes(meta), dtype=np.uint8)
+    out = np.empty(L.ZraShardHeaderSize(sizes.size, m.size), np.uint8)
+    st = L.ZraShardBuildHeader(uncompressed_size, frame_size, m.ctypes.data_as(C.c_void_p) if m.size else None, m.size,
+                               sizes.ctypes.data_as(C.POINTER(C.c_uint64)), sizes.size, out.ctypes.data_as(C.c_void_p), out.size)
+    if st.zra != 0:
+        raise binding.ZraError(st.zra, st.zstd)
+    return out
+
+
+def exchange_frame_sizes(local_sizes, frames, group=None):
+    """The compress path's one exchange step. Every rank contributes the compressed sizes of its frames
+    (in order); returns (all sizes in archive order, this shard's base offset, total compressed bytes).
+    The base offset is the exclusive scan of the per-shard totals."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    counts = [frame_range(frames, r, world)[1] - frame_range(frames, r, world)[0] for r in range(world)]
+    width = max(counts) if counts else 0
+    mine = torch.zeros(max(width, 1), dtype=torch.int64, device=dev)
+    local = np.ascontiguousarray(local_sizes, dtype=np.uint64)
+    assert local.size == counts[rank], (local.size, counts[rank])
+    if local.size:
+        mine[: local.size] = torch.from_numpy(local.view(np.int64)).to(dev)
+    gathered = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine, group=group)
+    parts = [g[: counts[r]].cpu().numpy().view(np.uint64) for r, g in enumerate(gathered)]
+    totals = np.array([int(p.sum()) for p in parts], dtype=np.uint64)
+    base = int(totals[:rank].sum())
+    return np.concatenate(parts) if parts else np.zeros(0, np.uint64), base, int(totals.sum())
+
+
+def compress_shard(ctx, d_in, in_size, frame_size, level, checksum, d_out, out_capacity, stream=0):
+    """ZraCudaCompressFrames on this rank's shard: returns (per-frame sizes, bytes produced)."""
+    L = binding.lib()
+    frames = (in_size + frame_size - 1) // frame_size
+    sizes = np.zeros(max(frames, 1), np.uint64)
+    produced = C.c_size_t(0)
+    st = L.ZraCudaCompressFrames(ctx._c, C.c_void_p(d_in), in_size, frame_size, level, checksum, C.c_void_p(d_out), out_capacity,
+                                 sizes.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(produced), C.c_void_p(stream))
+    ctx._raise(st)
+    return sizes[:frames], produced.value
