@@ -32,11 +32,17 @@ extern "C" __attribute__((visibility("default"))) long long sim_decode_frames(co
       block_setup(src, d, c, tabs[f], round == 0);
       if (c.blkType == BT_NONE) break;
       if (c.blkType == BT_COMPRESSED) {
-        if (c.litMode == LIT_HUF)
+        if (c.litMode == LIT_HUF) {
+          // the Huffman stage builds the two-level table from the weights (a 512-entry slot in the kernel,
+          // the per-frame global area when it does not fit)
+          HufLevels lv;
+          if (!huf_build_two_level(tabs[f].huf, 512, tabs[f].hufWeights, c.hufCount, c.hufLog, &lv))
+            huf_build_two_level(tabs[f].huf, kHufGlobalCap, tabs[f].hufWeights, c.hufCount, c.hufLog, &lv);
           for (u32 s = 0; s < c.nStreams; s++) {
-            u32 e = huf_stream(src, d, c, tabs[f].huf, lit.data(), s);
+            u32 e = huf_stream(src, d, c, tabs[f].huf, lv, lit.data(), s);
             if (e) frame_fail(c, e);
           }
+        }
         if (c.status) break;
         seq_decode(src, d, c, tabs[f], seqs.data(), seqCap);
         if (c.status) break;

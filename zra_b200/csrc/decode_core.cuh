@@ -56,15 +56,17 @@ struct FrameCtx {
   u32 strOff[4], strLen[4];
   u32 nbSeq, seqOff, seqLen;
   u32 llLog, ofLog, mlLog;
-  u32 pad;
+  u32 hufCount;  // number of Huffman weights (FrameTables::hufWeights), the implied last one included
 };
 
 // Table scratch of one frame (HBM). The sequence tables use the compact 2-byte format.
+constexpr u32 kHufGlobalCap = 4096 + 256;  // two-level table of any legal code (log <= 12): L1 256 + L2 < 4096
 struct FrameTables {
   CSym ll[512];
   CSym ml[512];
   CSym of[256];
-  HufSym huf[4096];
+  u8 hufWeights[256];        // weights of the current Huffman tree (kept across blocks for treeless literals)
+  HufSym huf[kHufGlobalCap]; // only used by frames whose two-level table does not fit its shared-memory slot
 };
 
 ZRA_DEV void frame_fail(FrameCtx& c, u32 code) {
@@ -182,7 +184,10 @@ ZRA_DEV void block_setup(const u8* srcBase, const FrameDesc& d, FrameCtx& c, Fra
         u8 weights[256];
         u32 count, log;
         u32 h = huf_read_weights(srcBase, d.srcOff + hoff, hlen, weights, &count, &log);
-        if (!h || !huf_build_table(t.huf, weights, count, log)) { frame_fail(c, ZE_CORRUPTION); return; }
+        if (!h || !huf_check_weights(weights, count)) { frame_fail(c, ZE_CORRUPTION); return; }
+        // the decode table itself is built by the Huffman stage, straight into shared memory
+        for (u32 i = 0; i < count; i++) t.hufWeights[i] = weights[i];
+        c.hufCount = count;
         c.hufLog = log;
         c.flags |= FF_HUF_VALID;
         hoff += h; hlen -= h;
@@ -265,41 +270,8 @@ ZRA_DEV void block_setup(const u8* srcBase, const FrameDesc& d, FrameCtx& c, Fra
   }
 }
 
-// ---------------------------------------------------------------- huf_stream (1 thread / stream)
-// Decodes stream `s` of the current block of one frame into the frame's literal scratch.
-// Returns 0 or a ZErr.
-ZRA_DEV u32 huf_stream(const u8* srcBase, const FrameDesc& d, const FrameCtx& c, const HufSym* table, u8* lit, u32 s) {
-  u32 seg = c.nStreams == 4 ? (c.litSize + 3) / 4 : c.litSize;
-  u32 outBeg = s * seg;
-  u32 n = (c.nStreams == 4 && s == 3) ? c.litSize - 3 * seg : seg;
-  BackReader br;
-  if (!br.init(srcBase, d.srcOff + c.strOff[s], c.strLen[s])) return ZE_CORRUPTION;
-  const u32 log = c.hufLog;
-  u8* out = lit + outBeg;
-  for (u32 i = 0; i < n; i++) {
-    br.refill();
-    HufSym e = table[br.peek(log)];
-    br.skip(e >> 8);
-    out[i] = (u8)e;
-  }
-  return br.remaining == 0 ? ZE_OK : ZE_CORRUPTION;
-}
-
-// ---------------------------------------------------------------- seq_decode (1 thread / frame)
-// Sequence records handed to seq_execute are CUMULATIVE, so the executor needs no prefix scans:
-//   litEnd (18 bits) | outEnd (18 bits) << 18 | offset (28 bits) << 36
-// litEnd = literals consumed by sequences 0..i of the block, outEnd = bytes regenerated by them
-// (both <= 128 KiB = 2^17, hence 18 bits), offset = the resolved match distance (repcodes done).
-ZRA_DEV u64 seq_pack(u32 ll, u32 ml, u32 off) { return (u64)ll | ((u64)ml << 18) | ((u64)off << 36); }
-ZRA_DEV u32 seq_ll(u64 s) { return (u32)s & 0x3FFFFu; }
-ZRA_DEV u32 seq_ml(u64 s) { return (u32)(s >> 18) & 0x3FFFFu; }
-ZRA_DEV u32 seq_off(u64 s) { return (u32)(s >> 36); }
-ZRA_DEV u32 rec_lit_end(u64 s) { return (u32)s & 0x3FFFFu; }
-ZRA_DEV u32 rec_out_end(u64 s) { return (u32)(s >> 18) & 0x3FFFFu; }
-ZRA_DEV u32 rec_off(u64 s) { return (u32)(s >> 36); }
-constexpr u32 kMaxOffset = (1u << 28) - 1;
-
-// Backward bit reader of the sequence stream, built for 32 unrelated streams advancing in
+// ---------------------------------------------------------------- bit reader
+// Backward bit reader of the sequence stream and of the Huffman streams, built for 32 unrelated streams advancing in
 // lock-step in one warp. SIMT facts that shape it (measured, profiles/r01b): a data-dependent
 // refill branch is taken by SOME lane at every step, so its body runs every step with two or
 // three lanes active; and a per-lane register prefetch does not work, because the scoreboard is
@@ -404,6 +376,69 @@ ZRA_DEV u32 win_take(u32& hi, u32& lo, u32 n) {
   lo = fsh_lc(0, lo, n);
   return v;
 }
+
+// ---------------------------------------------------------------- Huffman literals
+// Four symbols off a 64-bit window; returns them packed little-endian, *used = bits consumed.
+// At most 4 x 12 bits, so one window serves the group.
+ZRA_DEV u32 huf_group4(const HufSym* tab, const HufLevels& lv, u32 hi, u32 lo, u32* used) {
+  u32 word = 0, total = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (u32 j = 0; j < 4; j++) {
+    const u32 e = huf_lookup(tab, lv, hi);
+    const u32 nb = e >> 8;
+    word |= (e & 0xFFu) << (8 * j);
+    hi = fsh_lc(lo, hi, nb);
+    lo = fsh_lc(0, lo, nb);
+    total += nb;
+  }
+  *used = total;
+  return word;
+}
+
+// Thread-serial decode of stream `s` of the current block of one frame into its literal scratch,
+// with the same reader, table and group structure as k_huf_decode (host logic tests). 0 or a ZErr.
+ZRA_DEV u32 huf_stream(const u8* srcBase, const FrameDesc& d, const FrameCtx& c, const HufSym* tab, const HufLevels& lv, u8* lit,
+                       u32 s) {
+  u32 seg = c.nStreams == 4 ? (c.litSize + 3) / 4 : c.litSize;
+  u32 n = (c.nStreams == 4 && s == 3) ? c.litSize - 3 * seg : seg;
+  u32 ring[kRingWords];
+  SeqReader br;
+  if (!br.init(srcBase, d.srcOff + c.strOff[s], c.strLen[s], ring, 1)) return ZE_CORRUPTION;
+  u8* out = lit + s * seg;
+  u32 i = 0, it = 0;
+  while (i < n) {
+    if ((it++ & 1) == 0) br.refill_point();
+    u32 hi, lo, used;
+    br.window(hi, lo);
+    if (n - i >= 4) {
+      u32 w = huf_group4(tab, lv, hi, lo, &used);
+      out[i] = (u8)w; out[i + 1] = (u8)(w >> 8); out[i + 2] = (u8)(w >> 16); out[i + 3] = (u8)(w >> 24);
+      i += 4;
+    } else {
+      const u32 e = huf_lookup(tab, lv, hi);
+      used = e >> 8;
+      out[i++] = (u8)e;
+    }
+    br.p -= (i32)used;
+  }
+  return br.p == br.b0 ? ZE_OK : ZE_CORRUPTION;
+}
+
+// ---------------------------------------------------------------- seq_decode (1 thread / frame)
+// Sequence records handed to seq_execute are CUMULATIVE, so the executor needs no prefix scans:
+//   litEnd (18 bits) | outEnd (18 bits) << 18 | offset (28 bits) << 36
+// litEnd = literals consumed by sequences 0..i of the block, outEnd = bytes regenerated by them
+// (both <= 128 KiB = 2^17, hence 18 bits), offset = the resolved match distance (repcodes done).
+ZRA_DEV u64 seq_pack(u32 ll, u32 ml, u32 off) { return (u64)ll | ((u64)ml << 18) | ((u64)off << 36); }
+ZRA_DEV u32 seq_ll(u64 s) { return (u32)s & 0x3FFFFu; }
+ZRA_DEV u32 seq_ml(u64 s) { return (u32)(s >> 18) & 0x3FFFFu; }
+ZRA_DEV u32 seq_off(u64 s) { return (u32)(s >> 36); }
+ZRA_DEV u32 rec_lit_end(u64 s) { return (u32)s & 0x3FFFFu; }
+ZRA_DEV u32 rec_out_end(u64 s) { return (u32)(s >> 18) & 0x3FFFFu; }
+ZRA_DEV u32 rec_off(u64 s) { return (u32)(s >> 36); }
+constexpr u32 kMaxOffset = (1u << 28) - 1;
 
 // Per-frame state of the sequence stage; lives in registers of the lane that owns the frame.
 struct SeqState {

@@ -77,27 +77,35 @@ __global__ void k_block_setup(const u8* __restrict__ src, const FrameDesc* __res
 }
 
 // ------------------------------------------------------------------------------------------
-// Huffman literals. One warp = 8 frame slots x 4 lanes (lane & 3 = stream). Each slot keeps the
-// frame's single-symbol decode table (<= 2^11 entries x 2 B) in shared memory; a quad whose four
-// streams are done pulls the next frame from the work list.
-constexpr u32 kHufSlotEntries = 2048;
-constexpr u32 kHufWarpSmem = 8 * kHufSlotEntries * sizeof(HufSym);  // 32 KiB
+// Huffman literals. One warp = 8 frame slots x 4 lanes (lane & 3 = stream). The quad leader BUILDS
+// the frame's decode table from its weights straight into the quad's shared-memory slot, in the
+// two-level form (entropy.cuh: typically < 0.8 KiB instead of 4 KiB), so that every frame in flight
+// on an SM keeps its table on chip; a tree that does not fit the 1 KiB slot is built in the frame's
+// global scratch instead and read through generic loads. The streams are read with the same
+// warp-synchronous ring reader as the sequence stream. Symbols are decoded in groups of four (one
+// 64-bit window, one aligned 32-bit store); the warp runs a uniform number of groups between checks.
+constexpr u32 kHufSlotEntries = 512;
+constexpr u32 kHufWarpSmem = 8 * kHufSlotEntries * sizeof(HufSym) + kRingWords * 32 * sizeof(u32);  // 10 KiB
 
 __global__ void __launch_bounds__(32) k_huf_decode(const u8* __restrict__ src, const FrameDesc* __restrict__ descs,
-                                                   FrameCtx* __restrict__ ctxs, const FrameTables* __restrict__ tabs,
+                                                   FrameCtx* __restrict__ ctxs, FrameTables* __restrict__ tabs,
                                                    u8* __restrict__ lit, u32 litStride, RoundWork* __restrict__ work,
                                                    const u32* __restrict__ hufList) {
   extern __shared__ __align__(16) u8 smem[];
   HufSym* slots = reinterpret_cast<HufSym*>(smem);
+  u32* ring = reinterpret_cast<u32*>(smem + 8 * kHufSlotEntries * sizeof(HufSym)) + threadIdx.x;  // [kRingWords][32]
   const u32 lane = threadIdx.x, quad = lane >> 2, s = lane & 3;
   const u32 total = work->hufCount;
-  const HufSym* table = nullptr;
+  const HufSym* table = slots;
+  HufLevels lv;
+  lv.log = lv.p = lv.nEsc = lv.l2 = 0;
   u32 frame = kNone;      // frame owned by this quad
   bool quadIdle = true;   // quad has no frame
   bool exhausted = false;
   bool laneDone = true;   // this lane's stream is finished (or it has none)
-  BackReader br;
-  u32 i = 0, n = 0, log = 0;
+  SeqReader br;
+  br.p = br.b0 = br.loadedW = br.reqW = 0;
+  u32 i = 0, n = 0;
   u8* out = nullptr;
   for (;;) {
     // ---- hand frames to idle quads
@@ -109,27 +117,26 @@ __global__ void __launch_bounds__(32) k_huf_decode(const u8* __restrict__ src, c
       }
       f = __shfl_sync(kFull, f, lane & ~3u);
       if (quadIdle && !exhausted && f == kNone) exhausted = true;
-      u32 got = __ballot_sync(kFull, f != kNone && s == 0);
-      while (got) {  // whole warp copies each new table into its slot
-        int leader = __ffs(got) - 1;
-        got &= got - 1;
-        u32 wf = __shfl_sync(kFull, f, leader);
-        u32 wlog = ctxs[wf].hufLog;
-        if (wlog <= 11) {
-          const uint4* g = reinterpret_cast<const uint4*>(tabs[wf].huf);
-          uint4* dsts = reinterpret_cast<uint4*>(slots + (leader >> 2) * kHufSlotEntries);
-          u32 vecs = (2u << wlog) >> 4;  // bytes / 16
-          if (vecs == 0) vecs = 1;
-          for (u32 k = lane; k < vecs; k += 32) dsts[k] = g[k];
-        }
+      u32 where = 0;  // 1: shared-memory slot, 2: global scratch
+      if (f != kNone && s == 0) {
+        const FrameCtx& c = ctxs[f];
+        HufSym* slot = slots + quad * kHufSlotEntries;
+        if (huf_build_two_level(slot, kHufSlotEntries, tabs[f].hufWeights, c.hufCount, c.hufLog, &lv)) where = 1;
+        else { huf_build_two_level(tabs[f].huf, kHufGlobalCap, tabs[f].hufWeights, c.hufCount, c.hufLog, &lv); where = 2; }
       }
       __syncwarp();
+      {  // the leader's table description goes to its quad (all lanes take part in the shuffles)
+        const u32 leader = lane & ~3u;
+        const u32 w = __shfl_sync(kFull, where, leader);
+        const u32 a = __shfl_sync(kFull, lv.log, leader), b = __shfl_sync(kFull, lv.p, leader);
+        const u32 c = __shfl_sync(kFull, lv.nEsc, leader), d = __shfl_sync(kFull, lv.l2, leader);
+        if (f != kNone) { where = w; lv.log = a; lv.p = b; lv.nEsc = c; lv.l2 = d; }
+      }
       if (f != kNone) {
         frame = f;
         quadIdle = false;
         const FrameCtx& c = ctxs[f];
-        log = c.hufLog;
-        table = log <= 11 ? slots + quad * kHufSlotEntries : tabs[f].huf;
+        table = where == 1 ? slots + quad * kHufSlotEntries : tabs[f].huf;
         laneDone = true;
         if (s < c.nStreams) {
           u32 seg = c.nStreams == 4 ? (c.litSize + 3) / 4 : c.litSize;
@@ -137,43 +144,57 @@ __global__ void __launch_bounds__(32) k_huf_decode(const u8* __restrict__ src, c
           out = lit + (u64)f * litStride + s * seg;
           i = 0;
           laneDone = false;
-          if (!br.init(src, descs[f].srcOff + c.strOff[s], c.strLen[s])) {
+          if (!br.init(src, descs[f].srcOff + c.strOff[s], c.strLen[s], ring, 32)) {
             atomicCAS(&ctxs[f].status, 0u, (u32)ZE_CORRUPTION);
             laneDone = true;
-          }
-          if (n == 0 && !laneDone) {  // an empty stream still has to be a bare end mark
-            if (br.remaining != 0) atomicCAS(&ctxs[f].status, 0u, (u32)ZE_CORRUPTION);
-            laneDone = true;
+          } else {
+            // head: bring the output cursor to a 4-byte boundary so that the groups store whole words
+            u32 head = (4u - (u32)(reinterpret_cast<uintptr_t>(out) & 3u)) & 3u;
+            if (head > n) head = n;
+            for (; i < head; i++) {
+              u32 hi, lo;
+              br.window(hi, lo);
+              const u32 e = huf_lookup(table, lv, hi);
+              out[i] = (u8)e;
+              br.p -= (i32)(e >> 8);
+            }
           }
         }
       }
     }
     if (__all_sync(kFull, quadIdle)) break;
-    // ---- up to 4 symbols per lane; a full aligned group is stored as one 32-bit word
-    if (!laneDone) {
-      u32 k = 4 - ((u32)(uintptr_t)(out + i) & 3u);
-      if (k > n - i) k = n - i;
-      u32 word = 0;
-#pragma unroll
-      for (u32 j = 0; j < 4; j++) {
-        if (j < k) {
-          if ((j & 1) == 0) br.refill();
-          HufSym e = table[br.peek(log)];
-          br.skip(e >> 8);
-          word |= (u32)(e & 0xFFu) << (8 * j);
+    // ---- a warp-uniform number of 4-symbol groups
+    const u32 steps = __reduce_min_sync(kFull, laneDone ? 0xFFFFFFFFu : (n - i) >> 2);
+    if (!laneDone && steps != 0xFFFFFFFFu) {
+      u32* o4 = reinterpret_cast<u32*>(out + i);
+#pragma unroll 1
+      for (u32 k = 0; k < steps; k += 2) {
+        br.refill_point();  // at most 2 x 48 bits between points
+        u32 hi, lo, used;
+        br.window(hi, lo);
+        *o4++ = huf_group4(table, lv, hi, lo, &used);
+        br.p -= (i32)used;
+        if (k + 1 < steps) {
+          br.window(hi, lo);
+          *o4++ = huf_group4(table, lv, hi, lo, &used);
+          br.p -= (i32)used;
         }
       }
-      if (k == 4) {
-        *reinterpret_cast<u32*>(out + i) = word;
-      } else {
-        for (u32 j = 0; j < k; j++) out[i + j] = (u8)(word >> (8 * j));
-      }
-      i += k;
-      if (i >= n) {
+      i += 4 * steps;
+      if (n - i < 4) {  // tail, then the stream must be exactly used up
+        br.refill_point();
+        for (; i < n; i++) {
+          u32 hi, lo;
+          br.window(hi, lo);
+          const u32 e = huf_lookup(table, lv, hi);
+          out[i] = (u8)e;
+          br.p -= (i32)(e >> 8);
+        }
         laneDone = true;
-        if (br.remaining != 0) atomicCAS(&ctxs[frame].status, 0u, (u32)ZE_CORRUPTION);
+        if (br.p != br.b0) atomicCAS(&ctxs[frame].status, 0u, (u32)ZE_CORRUPTION);
       }
     }
+    __syncwarp();
     u32 dm = __ballot_sync(kFull, laneDone);
     if (!quadIdle && ((dm >> (lane & ~3u)) & 0xFu) == 0xFu) quadIdle = true;
   }
@@ -750,7 +771,7 @@ void launch_decode_rounds(const void* src, void* dst, u32 nFrames, u32 rounds, b
   const u8* in = static_cast<const u8*>(src);
   const u32 sms = (u32)sm_count();
   // persistent grids: as many warps as fit the SMs' shared memory, never more than there is work
-  const u32 hufWarps = sms * 6 < div_up(nFrames, 8) ? sms * 6 : div_up(nFrames, 8);
+  const u32 hufWarps = sms * 20 < div_up(nFrames, 8) ? sms * 20 : div_up(nFrames, 8);
   const u32 seqCtas = sms < div_up(nFrames, kSeqSlots) ? sms : div_up(nFrames, kSeqSlots);
   for (u32 r = 0; r < rounds; r++) {
     cudaMemsetAsync(work, 0, sizeof(RoundWork), st);

@@ -221,6 +221,63 @@ ZRA_DEV u32 huf_read_weights(const u8* base, u64 off, u32 len, u8* weights, u32*
   return consumed + 1;
 }
 
+// Two-level form of the same single-symbol table, small enough that every frame in flight keeps
+// its table in shared memory (a 2^11-entry table is 4 KiB; this is typically < 0.8 KiB):
+//   L1  2^p entries, p = min(log, 8), indexed by the next p bits. Codes of at most p bits resolve here.
+//   L2  the first l2 entries of the FULL 2^log table, indexed by the next log bits. zstd fills the
+//       table by ascending weight, i.e. the codes LONGER than p bits occupy exactly its first l2
+//       entries, and l2 is a multiple of 2^(log-p): L1 cells below nEsc = l2 >> (log-p) escape to L2.
+// Layout in `tab`: L1 at [0, 2^p), L2 at [2^p, 2^p + l2). Returns false when cap entries do not hold it.
+struct HufLevels {
+  u32 log, p, nEsc, l2;
+};
+ZRA_DEV bool huf_build_two_level(HufSym* tab, u32 cap, const u8* weights, u32 count, u32 log, HufLevels* lv) {
+  const u32 p = log < 8 ? log : 8;
+  const u32 drop = log - p;  // a code of weight w has log+1-w bits: longer than p <=> w <= drop
+  u32 rank[16];
+  for (u32 r = 0; r < 16; r++) rank[r] = 0;
+  for (u32 i = 0; i < count; i++) rank[weights[i]]++;
+  u32 start[16], nxt = 0;
+  for (u32 r = 1; r <= log; r++) {
+    start[r] = nxt;
+    nxt += rank[r] << (r - 1);
+  }
+  const u32 l2 = drop ? start[drop + 1] : 0;
+  lv->log = log; lv->p = p; lv->l2 = l2; lv->nEsc = l2 >> drop;
+  if ((1u << p) + l2 > cap) return false;
+  HufSym* l1 = tab;
+  HufSym* t2 = tab + (1u << p);
+  for (u32 s = 0; s < count; s++) {
+    u32 wt = weights[s];
+    if (!wt) continue;
+    u32 span = (1u << wt) >> 1;
+    HufSym e = (HufSym)(s | ((log + 1 - wt) << 8));
+    u32 b = start[wt];
+    start[wt] = b + span;
+    if (wt <= drop) {
+      for (u32 u = 0; u < span; u++) t2[b + u] = e;
+    } else {
+      u32 c0 = b >> drop, cn = span >> drop;
+      for (u32 u = 0; u < cn; u++) l1[c0 + u] = e;
+    }
+  }
+  return true;
+}
+// One symbol off the top of a left-justified 32-bit window `hi`: returns the table entry.
+ZRA_DEV u32 huf_lookup(const HufSym* tab, const HufLevels& lv, u32 hi) {
+  const u32 i8 = fsh_lc(hi, 0, lv.p);
+  const u32 iL = fsh_lc(hi, 0, lv.log);
+  const u32 idx = i8 < lv.nEsc ? (1u << lv.p) + iL : i8;
+  return tab[idx];
+}
+
+// Validates a weight set the way HUF_readDTableX1_wksp does (huf_decompress.c:140-149).
+ZRA_DEV bool huf_check_weights(const u8* weights, u32 count) {
+  u32 w1 = 0;
+  for (u32 i = 0; i < count; i++) w1 += weights[i] == 1;
+  return w1 >= 2 && !(w1 & 1);
+}
+
 // Fills the 1<<log entry single-symbol table: ascending weight, then ascending symbol.
 ZRA_DEV bool huf_build_table(HufSym* table, const u8* weights, u32 count, u32 log) {
   u32 rank[16];
