@@ -43,6 +43,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ra", action="store_true", help="skip the batched random-access leg")
     ap.add_argument("--ra-size-mib", type=int, default=1024, help="original bytes of the random-access archive (16 KiB frames)")
+    ap.add_argument("--no-compress", action="store_true", help="skip the CompressBuffer leg")
+    ap.add_argument("--compress-size-mib", type=int, default=1024, help="bytes of mixed data per GPU for the CompressBuffer leg")
     return ap.parse_args()
 
 
@@ -263,6 +265,105 @@ def run_ra(args, torch, dist, ctx, rank, world, peak):
     return out
 
 
+# ---------------------------------------------------------------- CompressBuffer (BASELINE configs[2] shape)
+def run_compress(args, torch, dist, ctx, rank, world, peak):
+    """CompressBuffer of mixed synthetic data (64 KiB runs of Zipf text alternating with incompressible bytes), 64 KiB
+    frames, levels 3 and 1, checksums. configs[2] is 8 GiB sharded over the GPUs of the box; here compress-size-mib per
+    GPU (1 GiB = the per-GPU shard of the 8-GPU case). The archive is verified by the REFERENCE decoder (oracle/_ref)."""
+    import ctypes as C
+
+    import refzra
+    import zra_b200
+    from zra_b200 import synth
+
+    fs = 65536
+    size = args.compress_size_mib << 20
+    data = synth.mixed(size, period=fs, seed=7 + rank)
+    d_in = torch.from_numpy(data).cuda()
+    cap = zra_b200_cap(size, fs)
+    d_out = torch.empty(cap + 64, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream()
+    out = {"metric": "compress GB/s", "unit": "GB/s", "config": {
+        "workload": f"CompressBuffer, {args.compress_size_mib} MiB per GPU of mixed data (64 KiB text / 64 KiB incompressible "
+                    "alternating), 65536 B frames, checksums", "value_definition": "input (uncompressed) bytes per second, all GPUs"},
+        "levels": {}}
+    for level in (3, 1):
+        def step():
+            return ctx.compress_buffer(d_in.data_ptr(), size, d_out.data_ptr(), cap, level=level, frame_size=fs, checksum=True,
+                                       stream=stream.cuda_stream)
+        t0 = time.perf_counter()
+        n = step()
+        torch.cuda.synchronize()
+        first = time.perf_counter() - t0
+        archive = d_out[:n].cpu().numpy()
+        if rank == 0 and refzra.have_ref():  # the unmodified reference must decode what the GPU wrote
+            back = np.zeros(size, np.uint8)
+            st = (C.c_int * 2)()
+            rc = refzra.ref().ref_decompress_mt(refzra._p(archive), archive.size, refzra._p(back), back.size, os.cpu_count() or 1, st)
+            assert rc == 0 and np.array_equal(back, data), f"reference decoder rejects the GPU archive (level {level}): {list(st)}"
+        steps = max(1, min(args.steps, int(3.0 / max(first, 1e-3))))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0.record(stream)
+        for _ in range(steps):
+            step()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item()) / steps
+        alg = size + n
+        res = {"value": round(world * size / (ms / 1e3) / 1e9, 3), "ms_per_step": round(ms, 3), "steps": steps, "archive_bytes": int(n),
+               "ratio": round(size / n, 4),
+               "roofline": {"bound": "hbm", "achieved": round(alg / (ms / 1e3) / 1e9, 2), "peak": peak, "unit": "GB/s",
+                            "frac": round(alg / (ms / 1e3) / 1e9 / peak, 6), "algorithmic_bytes_per_step": int(alg)}}
+        if rank == 0 and world == 1:
+            # end to end: ZraCompressBuffer with pinned host buffers
+            L = zra_b200.lib()
+            h_in = torch.from_numpy(data).pin_memory()
+            h_out = torch.empty(cap, dtype=torch.uint8).pin_memory()
+            osz = C.c_size_t(0)
+            def e2e_step():
+                st = L.ZraCompressBuffer(C.c_void_p(h_in.data_ptr()), size, C.c_void_p(h_out.data_ptr()), C.byref(osz), level, fs, True, None, 0)
+                assert st.zra == 0, (st.zra, st.zstd)
+            e2e_step()
+            k = max(1, min(steps, 3))
+            t0 = time.perf_counter()
+            for _ in range(k):
+                e2e_step()
+            dt = (time.perf_counter() - t0) / k
+            res["e2e"] = {"value": round(size / dt / 1e9, 3), "unit": "GB/s", "h2d_bytes_per_step": size, "d2h_bytes_per_step": int(osz.value),
+                          "api": "ZraCompressBuffer (host pointers, pinned)"}
+            del h_in, h_out
+            if not args.no_cpu_baseline and refzra.have_ref():
+                # the reference compressor on a bounded sample (first 256 MiB) with all host threads: ratio and GB/s
+                sample = min(size, 256 << 20)
+                threads = os.cpu_count() or 1
+                t0 = time.perf_counter()
+                ref_arch = refzra.ref_compress_mt(data[:sample], level, fs, True, threads)
+                dtc = time.perf_counter() - t0
+                gpu_sample = ctx.compress_buffer(d_in.data_ptr(), sample, d_out.data_ptr(), cap, level=level, frame_size=fs, checksum=True,
+                                                 stream=stream.cuda_stream)
+                res["ratio_vs_reference"] = {"sample_bytes": sample, "reference_archive_bytes": int(ref_arch.size),
+                                             "gpu_archive_bytes": int(gpu_sample),
+                                             "size_delta": round(gpu_sample / ref_arch.size - 1.0, 5)}
+                res["cpu_baseline"] = {"value": round(sample / dtc / 1e9, 4), "unit": "GB/s", "cores": threads, "kind": "reference",
+                                       "sample": f"the first {sample >> 20} MiB, {threads} host threads each with its own zra::Compressor "
+                                                 "(includes stitching the seek table)"}
+        out["levels"][f"L{level}"] = res
+    out["value"] = out["levels"]["L3"]["value"]
+    del d_in, d_out
+    return out
+
+
+def zra_b200_cap(size, frame_size):
+    import zra_b200
+    return int(zra_b200.GetOutputBufferSize(size, frame_size))
+
+
 # ---------------------------------------------------------------- GPU arm
 def run_gpu(args):
     import torch
@@ -397,6 +498,14 @@ def run_gpu(args):
         torch.cuda.empty_cache()
         ra = run_ra(args, torch, dist, ctx, rank, world, peak)
 
+    comp = None
+    if not args.no_compress:
+        torch.cuda.empty_cache()
+        try:
+            comp = run_compress(args, torch, dist, ctx, rank, world, peak)
+        except Exception as e:  # never take the headline down
+            comp = {"metric": "compress GB/s", "value": None, "unit": "GB/s", "error": repr(e)}
+
     if rank == 0:
         line = {
             "metric": "decompress GB/s", "value": round(value, 3), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
@@ -419,6 +528,8 @@ def run_gpu(args):
         }
         if ra is not None:
             line["random_access"] = ra
+        if comp is not None:
+            line["compress"] = comp
         if world == 1 and not args.no_cpu_baseline:
             try:
                 threads = os.cpu_count() or 1
