@@ -27,7 +27,7 @@ extern "C" __attribute__((visibility("default"))) long long sim_encode_frame(con
   EncScratch s;
   s.tabS = tabS.data(); s.tabL = tabL.data(); s.seqs = seqs.data(); s.lit = lit.data(); s.hist = hist.data();
   s.hcodes = hcodes.data(); s.hufOut = hufOut.data(); s.hufStride = blk + 64; s.hdr = hdr.data(); s.tt = tt.data();
-  s.states = states.data(); s.seqOut = seqOut.data(); s.seqOutCap = (u32)seqOut.size(); s.cells = cells.data();
+  s.states = states.data(); s.seqOut = seqOut.data(); s.seqOutCap = (u32)seqOut.size(); s.cells = cells.data(); s.cnt = nullptr;
   EncCtx c;
   memset(&c, 0, sizeof(c));
   c.srcLen = n;

@@ -80,7 +80,8 @@ def test_ratio_within_3_percent_of_reference(kind, fs, lvl):
     ref = refzra.ref_compress_mt(data, lvl, fs, True)
     assert np.array_equal(refzra.ref_decompress(ours), data)
     delta = ours.size / ref.size - 1
-    assert abs(delta) < 0.03, (ours.size, ref.size, delta)
+    # never more than 3 % larger than the reference; the parallel matcher inserts every position, so it may be smaller
+    assert -0.10 < delta < 0.03, (ours.size, ref.size, delta)
     # the headers have the same length and, apart from hash and table values, the same bytes
     ho, hr = parse_header(ours), parse_header(ref)
     for k in ("frameId", "headerSize", "magic", "version", "uncompressedSize", "tableSize", "frameSize", "metaSize"):

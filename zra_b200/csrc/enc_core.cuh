@@ -101,6 +101,7 @@ struct EncScratch {
   u8* seqOut;        // sequence bitstream
   u32 seqOutCap;
   u8* cells;         // 1 KiB of spread / weight-coding scratch
+  u32* cnt;          // LL[36] | OF[32] | ML[53] code counts when the matcher already made them, else null
 };
 
 // ------------------------------------------------------------------ unaligned reads of the input
@@ -364,11 +365,17 @@ ZRA_DEV void enc_plan(EncCtx& c, const EncScratch& s) {
   for (u32 k = 0; k < 36; k++) cntLL[k] = 0;
   for (u32 k = 0; k < 32; k++) cntOF[k] = 0;
   for (u32 k = 0; k < 53; k++) cntML[k] = 0;
-  for (u32 i = 0; i < nbSeq; i++) {
-    u64 q = s.seqs[i];
-    cntLL[ll_code(seq_ll(q))]++;
-    cntOF[of_code(seq_off(q))]++;
-    cntML[ml_code(seq_ml(q) - 3)]++;
+  if (s.cnt) {
+    for (u32 k = 0; k < 36; k++) cntLL[k] = s.cnt[k];
+    for (u32 k = 0; k < 32; k++) cntOF[k] = s.cnt[36 + k];
+    for (u32 k = 0; k < 53; k++) cntML[k] = s.cnt[68 + k];
+  } else {
+    for (u32 i = 0; i < nbSeq; i++) {
+      u64 q = s.seqs[i];
+      cntLL[ll_code(seq_ll(q))]++;
+      cntOF[of_code(seq_off(q))]++;
+      cntML[ml_code(seq_ml(q) - 3)]++;
+    }
   }
   const u32 modesPos = hp++;
   u32 modes = 0;

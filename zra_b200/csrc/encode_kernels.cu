@@ -13,6 +13,8 @@
 // (source/zra.cpp:216-225, 329-338). The thread bodies are in enc_core.cuh.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "enc_core.cuh"
 #include "encode_launch.h"
 
@@ -41,6 +43,7 @@ struct EncView {
     f.seqOut = s + lay.offSeqOut + (u64)i * lay.seqOutStride;
     f.seqOutCap = lay.seqOutStride;
     f.cells = s + lay.offCells + (u64)i * 1024;
+    f.cnt = lay.ctaMatch ? reinterpret_cast<u32*>(s + lay.offCnt) + (u64)i * 128 : nullptr;
     return f;
   }
   __device__ u8* out(u32 i) const { return s + lay.offOut + (u64)i * lay.outStride; }
@@ -89,6 +92,266 @@ __global__ void k_enc_match(EncJob j, EncView v, u32 round) {
     enc_match(j.in, j.inOff + (u64)i * j.frameSize, p, c, v.frame(i));
   }
   v.ctx(i) = c;
+}
+
+// ------------------------------------------------------------------------------------------
+// Frame-cooperative match finder (frames <= 64 KiB: one block, positions fit 16 bits).
+// One CTA per frame; the frame's hash tables live in shared memory as 16-bit positions (level 3,
+// 64 KiB frames: 2^15 short + 2^16 long entries = 192 KiB, i.e. one frame per SM). The block is
+// consumed in rounds of T = blockDim positions:
+//   A  every thread hashes its position (8-byte long hash, mls-byte short hash), reads the tables,
+//      inserts itself, and after a barrier reads again: the newest candidate BELOW its own position
+//      wins (all positions are inserted, unlike the serial reference matcher, which only inserts
+//      the positions it visits — the parse is at least as dense);
+//   B  every thread verifies its candidates against the input (L1/L2) and leaves the best
+//      (length <= kLaneLenCap, offset) in shared memory;
+//   C  warp 0 walks the round greedily with warp-uniform state: next position with a match by
+//      ballot/ffs, one-byte lazy step towards a long match, warp-wide extension of capped
+//      matches, repeat-offset coding, sequence record. Nothing in the walk waits for a load.
+// After the last round the whole CTA gathers the literals (one thread per sequence) and builds the
+// literal histogram and the LL / OF / ML code histograms in shared memory.
+// Replaces ZSTD_compressBlock_fast / _doubleFast for these frames (zstd_fast.c:46-183,
+// zstd_double_fast.c:50-316): same hash functions and minimum match lengths; a different
+// (parallel) visiting order, so the bytes differ from the reference's while the format, the
+// decoder and the ratio (tests: within 3 %) do not.
+constexpr u32 kLaneLenCap = 40;
+constexpr u32 kInfoMore = 0x80000000u;  // the lane stopped comparing before the first mismatch
+
+__device__ __forceinline__ u64 gld8(const u8* base, u64 off) {
+  const u32* w = reinterpret_cast<const u32*>(base) + (off >> 2);
+  const u32 sh = (u32)(off & 3) * 8;
+  const u32 a = __ldg(w), b = __ldg(w + 1), c = sh ? __ldg(w + 2) : 0u;
+  return (u64)__funnelshift_r(a, b, sh) | ((u64)__funnelshift_r(b, c, sh) << 32);
+}
+__device__ __forceinline__ u32 gld4(const u8* base, u64 off) {
+  const u32* w = reinterpret_cast<const u32*>(base) + (off >> 2);
+  const u32 sh = (u32)(off & 3) * 8;
+  const u32 a = __ldg(w), b = sh ? __ldg(w + 1) : 0u;
+  return __funnelshift_r(a, b, sh);
+}
+__device__ __forceinline__ u32 common8(u64 x) { return x ? ((u32)__ffsll((long long)x) - 1) >> 3 : 8u; }
+
+// Sequence codes (zstd_compress_internal.h: ZSTD_LLcode / ZSTD_MLcode), table-free.
+__device__ __forceinline__ u32 ll_code_fast(u32 ll) {
+  if (ll < 16) return ll;
+  if (ll >= 64) return highbit32(ll) + 19;
+  if (ll < 24) return 16 + ((ll - 16) >> 1);
+  if (ll < 32) return 20 + ((ll - 24) >> 2);
+  if (ll < 48) return 22 + ((ll - 32) >> 3);
+  return 24;
+}
+__device__ __forceinline__ u32 ml_code_fast(u32 mlBase) {  // mlBase = matchLength - 3
+  if (mlBase < 32) return mlBase;
+  if (mlBase >= 128) return highbit32(mlBase) + 36;
+  if (mlBase < 40) return 32 + ((mlBase - 32) >> 1);   // 35,37,39,41 -> codes 32..35
+  if (mlBase < 48) return 36 + ((mlBase - 40) >> 2);   // 43,47 -> 36,37
+  if (mlBase < 64) return 38 + ((mlBase - 48) >> 3);   // 51,59 -> 38,39
+  if (mlBase < 96) return 40 + ((mlBase - 64) >> 4);   // 67,83 -> 40,41
+  return 42;                                           // 99..130
+}
+
+__device__ __forceinline__ void table_insert_min(u16* cell, u32 pos, u32 roundBase) {
+  unsigned short cur = *cell;
+  while ((u16)(cur - roundBase) > (u16)(pos - roundBase)) {
+    const unsigned short prev = atomicCAS(reinterpret_cast<unsigned short*>(cell), cur, (unsigned short)pos);
+    if (prev == cur) break;
+    cur = prev;
+  }
+}
+
+template <int T>
+__global__ void __launch_bounds__(T) k_enc_match_cta(EncJob j, EncView v) {
+  extern __shared__ __align__(16) u8 smem[];
+  __shared__ u32 sAnchor;
+  __shared__ u32 sFinal[8];
+  const u32 i = blockIdx.x;
+  const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  EncCtx& gc = v.ctx(i);
+  const u32 len = gc.srcLen;
+  const u32 logS = v.lay.matchLogS, logL = v.lay.matchLogL, mls = v.lay.matchMls;
+  const bool dfast = logL != 0;
+  const u32 nS = 1u << logS, nL = dfast ? (1u << logL) : 0u;
+  u16* tabS = reinterpret_cast<u16*>(smem);
+  u16* tabL = tabS + nS;
+  u32* info = reinterpret_cast<u32*>(smem + 2ull * (nS + nL));
+  u32* hist = info + T;   // 256 literal counts, then 36 + 32 + 53 code counts
+  u32* cnt = hist + 256;
+  const u8* base = j.in;
+  const u64 fbase = j.inOff + (u64)i * j.frameSize;
+  const EncScratch s = v.frame(i);
+  u32* side = reinterpret_cast<u32*>(s.hufOut);  // per sequence: literal source | literal destination << 16
+  // ---- clear tables and histograms
+  {
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    const u32 n16 = (2u * (nS + nL)) >> 4;
+    for (u32 k = tid; k < n16; k += T) z[k] = make_uint4(0, 0, 0, 0);
+    for (u32 k = tid; k < 256 + 128; k += T) hist[k] = 0;
+    if (tid == 0) sAnchor = 0;
+  }
+  __syncthreads();
+  // selector state (meaningful in warp 0, warp-uniform)
+  EncCtx rc;
+  rc.rep[0] = 1; rc.rep[1] = 4; rc.rep[2] = 8;
+  u32 anchor = 0, nseq = 0, litPos = 0;
+  const u32 hashEnd = len >= 16 ? len - 8 : 0;  // positions below this can start a match (zstd: ip < iend - 8)
+  for (u32 rb = 0; rb < hashEnd; rb += T) {
+    const u32 pos = rb + tid;
+    const u32 curAnchor = sAnchor;
+    if (curAnchor >= rb + T) continue;  // the whole round lies inside a match already taken (uniform)
+    // ---- A: hash, read the pre-round candidates, then insert. The insert keeps the LOWEST position
+    // of this round per cell (16-bit compare-and-swap on the distance from the round base, under
+    // which every older entry ranks above the round's own), so the table — and with it the archive —
+    // does not depend on thread timing, and later positions of the round see an in-round candidate.
+    const bool live = pos < hashEnd;
+    u64 x = 0;
+    u32 hS = 0, hL = 0, cS = 0, cL = 0;
+    if (live) {
+      x = gld8(base, fbase + pos);
+      hS = mls <= 4 ? ((u32)x * 2654435761u) >> (32 - logS) : (u32)(((x << (64 - 8 * mls)) * 0x9E3779B97F4A7C15ull) >> (64 - logS));
+      cS = tabS[hS];
+      if (dfast) {
+        hL = (u32)((x * 0xCF1BBCDCB7A56463ull) >> (64 - logL));
+        cL = tabL[hL];
+      }
+    }
+    __syncthreads();
+    if (live) {
+      table_insert_min(&tabS[hS], pos, rb);
+      if (dfast) table_insert_min(&tabL[hL], pos, rb);
+    }
+    __syncthreads();
+    u32 e = 0;
+    if (live && pos >= curAnchor && pos > 0) {
+      u32 c2 = tabS[hS];
+      if (c2 < pos && c2 >= rb) cS = c2;
+      bool okS = cS < pos, okL = false;
+      if (dfast) {
+        c2 = tabL[hL];
+        if (c2 < pos && c2 >= rb) cL = c2;
+        okL = cL < pos;
+      }
+      // ---- B: verify
+      u32 bestLen = 0, bestOff = 0;
+      u32 nL8 = 0, nS8 = 0;
+      if (okL) nL8 = common8(gld8(base, fbase + cL) ^ x);
+      if (okS && (!okL || cS != cL)) nS8 = common8(gld8(base, fbase + cS) ^ x);
+      if (nL8 >= 4 && nL8 >= nS8) { bestLen = nL8; bestOff = pos - cL; }
+      else if (nS8 >= 4) { bestLen = nS8; bestOff = pos - cS; }
+      bool more = false;
+      if (bestLen == 8) {
+        const u32 cand = pos - bestOff;
+        more = true;
+        while (bestLen < kLaneLenCap && pos + bestLen + 8 <= len) {
+          const u32 c = common8(gld8(base, fbase + pos + bestLen) ^ gld8(base, fbase + cand + bestLen));
+          bestLen += c;
+          if (c < 8) { more = false; break; }
+        }
+      }
+      if (bestLen >= 4) e = bestOff | (bestLen << 16) | (more ? kInfoMore : 0u);
+    }
+    info[tid] = e;
+    __syncthreads();
+    // ---- C: greedy selection by warp 0
+    if (warp == 0) {
+      for (u32 g = 0; g < T / 32; g++) {
+        const u32 gb = rb + g * 32;
+        if (gb >= hashEnd) break;
+        if (anchor >= gb + 32) continue;
+        const u32 my = info[g * 32 + lane];
+        const u32 mask = __ballot_sync(kFullMask, my != 0);
+        for (;;) {
+          const u32 from = anchor > gb ? anchor - gb : 0;
+          if (from >= 32) break;
+          const u32 m = mask & (0xFFFFFFFFu << from);
+          if (!m) break;
+          u32 k = (u32)__ffs((int)m) - 1;
+          u32 ee = __shfl_sync(kFullMask, my, k);
+          if (k < 31 && ((mask >> (k + 1)) & 1u)) {
+            const u32 e2 = __shfl_sync(kFullMask, my, k + 1);
+            const u32 l1 = (ee >> 16) & 0xFFu, l2 = (e2 >> 16) & 0xFFu;
+            if (l1 < 8 && l2 >= 8) { ee = e2; k++; }
+          }
+          const u32 mpos = gb + k;
+          u32 ml = (ee >> 16) & 0xFFu;
+          const u32 off = ee & 0xFFFFu;
+          if (ee & kInfoMore) {
+            // warp-wide extension: 4 bytes per lane and trip
+            for (;;) {
+              const u32 a = mpos + ml + 4 * lane;
+              u32 diff = 0;  // byte k of diff != 0: byte k differs / is past the end
+              if (a + 4 <= len) {
+                diff = gld4(base, fbase + a) ^ gld4(base, fbase + a - off);
+              } else {
+                for (u32 b = 0; b < 4; b++) {
+                  if (a + b >= len || base[fbase + a + b] != base[fbase + a + b - off]) { diff = 0xFFu << (8 * b); break; }
+                }
+              }
+              const u32 bad = __ballot_sync(kFullMask, diff != 0);
+              if (!bad) { ml += 128; continue; }
+              const u32 first = (u32)__ffs((int)bad) - 1;
+              const u32 d = __shfl_sync(kFullMask, diff, first);
+              ml += 4 * first + (((u32)__ffs((int)d) - 1) >> 3);
+              break;
+            }
+          }
+          // ---- emit
+          const u32 ll = mpos - anchor;
+          const u64 rec = emit_sequence(rc, ll, ml, off);
+          if (lane == 0) {
+            s.seqs[nseq] = rec;
+            side[nseq] = anchor | (litPos << 16);
+          }
+          nseq++;
+          litPos += ll;
+          anchor = mpos + ml;
+        }
+      }
+      if (lane == 0) sAnchor = anchor;
+    }
+    __syncthreads();
+  }
+  // ---- literal gather + histograms (whole CTA), results
+  if (tid == 0) {
+    sFinal[0] = litPos; sFinal[1] = nseq; sFinal[2] = rc.rep[0]; sFinal[3] = rc.rep[1]; sFinal[4] = rc.rep[2];
+    __threadfence_block();
+  }
+  __syncthreads();
+  anchor = sAnchor;
+  litPos = sFinal[0];
+  nseq = sFinal[1];
+  __threadfence();  // the records / side entries were written by warp 0 through global memory
+  for (u32 q = tid; q < nseq; q += T) {
+    const u64 rec = s.seqs[q];
+    const u32 sd = side[q];
+    const u32 ll = seq_ll(rec), from = sd & 0xFFFFu, to = sd >> 16;
+    for (u32 k = 0; k < ll; k++) {
+      const u8 b = base[fbase + from + k];
+      s.lit[to + k] = b;
+      atomicAdd(&hist[b], 1u);
+    }
+    atomicAdd(&cnt[ll_code_fast(ll)], 1u);
+    atomicAdd(&cnt[36 + highbit32(seq_off(rec))], 1u);
+    atomicAdd(&cnt[68 + ml_code_fast(seq_ml(rec) - 3)], 1u);
+  }
+  const u32 rest = len - anchor;
+  for (u32 q = tid; q < rest; q += T) {
+    const u8 b = base[fbase + anchor + q];
+    s.lit[litPos + q] = b;
+    atomicAdd(&hist[b], 1u);
+  }
+  __syncthreads();
+  for (u32 k = tid; k < 256; k += T) s.hist[k] = hist[k];
+  for (u32 k = tid; k < 128; k += T) s.cnt[k] = cnt[k];
+  if (tid == 0) {
+    gc.blkActive = 1;
+    gc.blkPos = 0;
+    gc.blkLen = len;
+    gc.lastBlock = 1;
+    gc.repSave[0] = 1; gc.repSave[1] = 4; gc.repSave[2] = 8;
+    gc.rep[0] = sFinal[2]; gc.rep[1] = sFinal[3]; gc.rep[2] = sFinal[4];
+    gc.nbSeq = nseq;
+    gc.litSize = litPos + rest;
+  }
 }
 
 __global__ void k_enc_literals(EncJob j, EncView v) {
@@ -140,6 +403,258 @@ __global__ void k_enc_assemble(EncJob j, EncView v) {
   EncParams p = enc_params(j.level, c.srcLen, j.checksum != 0);
   enc_assemble(j.in, j.inOff + (u64)i * j.frameSize, p, c, v.frame(i), v.out(i));
   v.ctx(i) = c;
+}
+
+// ------------------------------------------------------------------------------------------
+// FSE sequence bitstream, one warp per frame. The three state chains (LL, OF, ML) are the only
+// serial part: lanes 0..2 run them over 32 sequences at a time with the encode tables in shared
+// memory and leave (bits, nbBits) per sequence; then all 32 lanes lay their sequence's bit string
+// (state bits + extra bits, <= 89 bits) at its prefix-summed bit offset in a shared-memory staging
+// window, and whole words leave with coalesced stores. Same bit order as enc_seq (enc_core.cuh),
+// i.e. ZSTD_encodeSequences (zstd_compress_sequences.c:286-359).
+constexpr u32 kSeqEncWarps = 8;
+struct SeqEncSmem {
+  FseSymTT tt[128];      // LL 0..35 | OF 36..67 | ML 68..120
+  u16 states[1280];      // LL 0..511 | OF 512..767 | ML 768..1279
+  u32 chain[3][32];      // bits | nbBits << 16 per sequence of the chunk
+  u32 stage[128];        // bit window of the chunk
+  u8 codes[3][32];
+};
+
+__device__ __forceinline__ void bits_append(u64& lo, u64& hi, u32& n, u32 val, u32 nb) {
+  if (n < 64) {
+    lo |= (u64)val << n;
+    if (n + nb > 64) hi |= (u64)val >> (64 - n);
+  } else {
+    hi |= (u64)val << (n - 64);
+  }
+  n += nb;
+}
+
+__global__ void __launch_bounds__(kSeqEncWarps * 32) k_enc_seq_warp(EncJob j, EncView v) {
+  __shared__ __align__(16) SeqEncSmem sm[kSeqEncWarps];
+  const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const u32 i = blockIdx.x * kSeqEncWarps + w;
+  if (i >= j.nFrames) return;
+  EncCtx& c = v.ctx(i);
+  if (!c.blkActive) return;
+  const u32 nbSeq = c.nbSeq;
+  if (!nbSeq) {
+    if (lane == 0) c.seqStreamSize = 0;
+    return;
+  }
+  SeqEncSmem& W = sm[w];
+  const EncScratch s = v.frame(i);
+  for (u32 k = lane; k < 121; k += 32) W.tt[k] = s.tt[k];
+  {
+    const u32* src = reinterpret_cast<const u32*>(s.states);
+    u32* dst = reinterpret_cast<u32*>(W.states);
+    for (u32 k = lane; k < 640; k += 32) dst[k] = src[k];
+  }
+  const u32 logLL = c.seqLog[0], logOF = c.seqLog[1], logML = c.seqLog[2];
+  const u32 ttBase = lane == 0 ? 0u : (lane == 1 ? 36u : 68u);
+  const u32 stBase = lane == 0 ? 0u : (lane == 1 ? 512u : 768u);
+  const u32 cl = lane < 3 ? lane : 0u;
+  u32 state = 0;
+  u32 carry = 0, carryBits = 0, outWords = 0;
+  u32* out32 = reinterpret_cast<u32*>(s.seqOut);
+  const u32 capWords = s.seqOutCap >> 2;
+  __syncwarp();
+  for (u32 done = 0; done < nbSeq; done += 32) {
+    const u32 count = nbSeq - done < 32 ? nbSeq - done : 32;
+    const bool valid = lane < count;
+    // ---- codes of this chunk (sequence nbSeq-1-done-lane: the stream is written last to first)
+    u32 ll = 0, mlb = 0, ov = 1, lc = 0, mc = 0, oc = 0;
+    if (valid) {
+      const u64 q = s.seqs[nbSeq - 1 - done - lane];
+      ll = seq_ll(q); mlb = seq_ml(q) - 3; ov = seq_off(q);
+      lc = ll_code_fast(ll); mc = ml_code_fast(mlb); oc = highbit32(ov);
+      W.codes[0][lane] = (u8)lc; W.codes[1][lane] = (u8)oc; W.codes[2][lane] = (u8)mc;
+    }
+    for (u32 k = lane; k < 128; k += 32) W.stage[k] = 0;
+    __syncwarp();
+    // ---- the three state chains
+    if (lane < 3) {
+      u32 t = 0;
+      if (done == 0) {  // the last sequence's symbols ride in the initial states
+        const FseSymTT e = W.tt[ttBase + W.codes[cl][0]];
+        const u32 nb = (e.deltaNbBits + (1u << 15)) >> 16;
+        const u32 value = (nb << 16) - e.deltaNbBits;
+        state = W.states[stBase + (u32)((i32)(value >> nb) + e.deltaFindState)];
+        W.chain[cl][0] = 0;
+        t = 1;
+      }
+#pragma unroll 4
+      for (; t < count; t++) {
+        const FseSymTT e = W.tt[ttBase + W.codes[cl][t]];
+        const u32 nb = (state + e.deltaNbBits) >> 16;
+        W.chain[cl][t] = (state & ((1u << nb) - 1u)) | (nb << 16);
+        state = W.states[stBase + (u32)((i32)(state >> nb) + e.deltaFindState)];
+      }
+    }
+    __syncwarp();
+    // ---- this lane's bit string: OF, ML, LL state bits, then LL, ML, OF extra bits
+    u64 lo = 0, hi = 0;
+    u32 n = 0;
+    if (valid) {
+      const u32 cLL = W.chain[0][lane], cOF = W.chain[1][lane], cML = W.chain[2][lane];
+      bits_append(lo, hi, n, cOF & 0xFFFFu, cOF >> 16);
+      bits_append(lo, hi, n, cML & 0xFFFFu, cML >> 16);
+      bits_append(lo, hi, n, cLL & 0xFFFFu, cLL >> 16);
+      bits_append(lo, hi, n, ll - kLLBase[lc], kLLBits[lc]);
+      bits_append(lo, hi, n, mlb + 3 - kMLBase[mc], kMLBits[mc]);
+      bits_append(lo, hi, n, ov - (1u << oc), oc);
+    }
+    u32 incl = n;
+#pragma unroll
+    for (u32 d = 1; d < 32; d <<= 1) {
+      const u32 up = __shfl_up_sync(kFullMask, incl, d);
+      if (lane >= d) incl += up;
+    }
+    const u32 total = __shfl_sync(kFullMask, incl, 31);
+    if (n) {
+      const u32 pos = carryBits + incl - n;
+      const u32 word = pos >> 5, sh = pos & 31u;
+      const u32 v0 = (u32)lo, v1 = (u32)(lo >> 32), v2 = (u32)hi;
+      const u32 o0 = v0 << sh, o1 = __funnelshift_l(v0, v1, sh), o2 = __funnelshift_l(v1, v2, sh), o3 = __funnelshift_l(v2, 0u, sh);
+      if (o0) atomicOr(&W.stage[word], o0);
+      if (o1) atomicOr(&W.stage[word + 1], o1);
+      if (o2) atomicOr(&W.stage[word + 2], o2);
+      if (o3) atomicOr(&W.stage[word + 3], o3);
+    }
+    if (lane == 0 && carryBits) atomicOr(&W.stage[0], carry);
+    __syncwarp();
+    const u32 totalBits = carryBits + total;
+    const u32 full = totalBits >> 5;
+    for (u32 k = lane; k < full; k += 32)
+      if (outWords + k < capWords) out32[outWords + k] = W.stage[k];
+    carry = W.stage[full];
+    carryBits = totalBits & 31u;
+    outWords += full;
+    __syncwarp();
+  }
+  // ---- final states (ML, OF, LL), end mark
+  const u32 stLL = __shfl_sync(kFullMask, state, 0), stOF = __shfl_sync(kFullMask, state, 1), stML = __shfl_sync(kFullMask, state, 2);
+  if (lane == 0) {
+    u64 acc = carryBits ? (u64)carry : 0ull;
+    u32 nb = carryBits;
+    acc |= (u64)(stML & ((1u << logML) - 1u)) << nb; nb += logML;
+    acc |= (u64)(stOF & ((1u << logOF) - 1u)) << nb; nb += logOF;
+    acc |= (u64)(stLL & ((1u << logLL) - 1u)) << nb; nb += logLL;
+    acc |= 1ull << nb; nb += 1;
+    const u32 bytes = (nb + 7) >> 3;
+    u32 pos = outWords * 4;
+    for (u32 k = 0; k < bytes; k++, pos++)
+      if (pos < s.seqOutCap) s.seqOut[pos] = (u8)(acc >> (8 * k));
+    c.seqStreamSize = pos;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Block assembly, one warp per frame: the decisions of enc_assemble (enc_core.cuh) taken
+// warp-uniformly, header bytes by lane 0, every section moved by the whole warp.
+__device__ __forceinline__ void warp_move(u8* dst, const u8* src, u32 n, u32 lane) {
+  // 32-bit stores to the aligned body of dst, source words funnel-shifted into place
+  u32 head = (4u - (u32)(reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u;
+  if (head > n) head = n;
+  if (lane < head) dst[lane] = src[lane];
+  dst += head; src += head; n -= head;
+  const u32 words = n >> 2;
+  const u32 sh = (u32)(reinterpret_cast<uintptr_t>(src) & 3u) * 8u;
+  const u32* sw = reinterpret_cast<const u32*>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)3);
+  u32* dw = reinterpret_cast<u32*>(dst);
+  for (u32 k = lane; k < words; k += 32) {
+    const u32 a = sw[k], b = sh ? sw[k + 1] : 0u;
+    dw[k] = __funnelshift_r(a, b, sh);
+  }
+  const u32 done = words << 2, tail = n & 3u;
+  if (lane < tail) dst[done + lane] = src[done + lane];
+}
+
+__global__ void __launch_bounds__(256) k_enc_assemble_warp(EncJob j, EncView v) {
+  const u32 i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (i >= j.nFrames) return;
+  EncCtx& gc = v.ctx(i);
+  if (!gc.blkActive) return;
+  const EncCtx c = gc;
+  const EncParams p = enc_params(j.level, c.srcLen, j.checksum != 0);
+  const EncScratch s = v.frame(i);
+  const u8* in = j.in + j.inOff + (u64)i * j.frameSize;
+  u8* out = v.out(i);
+  u32 op = c.outPos;
+#define ZRA_PUT(b) do { if (lane == 0) out[op] = (u8)(b); op++; } while (0)
+  if (c.blkPos == 0) {
+    op = 0;
+    ZRA_PUT(0x28); ZRA_PUT(0xB5); ZRA_PUT(0x2F); ZRA_PUT(0xFD);
+    ZRA_PUT(p.checksum << 2);
+    ZRA_PUT((c.windowLog - 10) << 3);
+  }
+  const u32 n = c.litSize;
+  u32 litMode = c.litMode;
+  u32 litSection = 0, cLit = 0;
+  if (litMode == 2) {
+    cLit = c.hufHeaderSize + (c.nStreams == 4 ? 6 : 0);
+    for (u32 k = 0; k < c.nStreams; k++) cLit += c.hufStreamSize[k];
+    const u32 lh = 3 + (n >= 1024) + (n >= 16384);
+    litSection = lh + cLit;
+    bool spilled = false;
+    for (u32 k = 0; k < c.nStreams; k++) spilled |= c.hufStreamSize[k] > s.hufStride;
+    if (spilled || litSection + ((n >> 6) + 2) >= n + 3 || cLit >= (1u << 18) ||
+        (c.nStreams == 4 && (c.hufStreamSize[0] > 65535 || c.hufStreamSize[1] > 65535 || c.hufStreamSize[2] > 65535)))
+      litMode = 0;
+  }
+  if (litMode == 0) litSection = (n < 32 ? 1 : (n < 4096 ? 2 : 3)) + n;
+  else if (litMode == 1) litSection = (n < 32 ? 1 : (n < 4096 ? 2 : 3)) + 1;
+  const u32 seqSection = c.seqHeaderSize + c.seqStreamSize;
+  const u32 cSize = litSection + seqSection;
+  const u32 minGain = (c.blkLen >> 6) + 2;
+  const bool raw = c.blkLen < 7 || cSize + minGain >= c.blkLen || cSize >= kBlockSizeMax || c.seqStreamSize > s.seqOutCap;
+  const u32 bsize = raw ? c.blkLen : cSize;
+  const u32 bh = (c.lastBlock ? 1u : 0u) | ((raw ? 0u : 2u) << 1) | (bsize << 3);
+  ZRA_PUT(bh); ZRA_PUT(bh >> 8); ZRA_PUT(bh >> 16);
+  if (raw) {
+    warp_move(out + op, in + c.blkPos, c.blkLen, lane);
+    op += c.blkLen;
+  } else {
+    if (litMode == 2) {
+      const u32 single = c.nStreams == 1;
+      if (n < 1024) {
+        const u32 x = 2u | ((single ? 0u : 1u) << 2) | (n << 4) | (cLit << 14);
+        ZRA_PUT(x); ZRA_PUT(x >> 8); ZRA_PUT(x >> 16);
+      } else if (n < 16384) {
+        const u32 x = 2u | (2u << 2) | (n << 4) | (cLit << 18);
+        ZRA_PUT(x); ZRA_PUT(x >> 8); ZRA_PUT(x >> 16); ZRA_PUT(x >> 24);
+      } else {
+        const u64 x = 2u | (3u << 2) | ((u64)n << 4) | ((u64)cLit << 22);
+        for (u32 k = 0; k < 5; k++) ZRA_PUT(x >> (8 * k));
+      }
+      warp_move(out + op, s.hdr, c.hufHeaderSize, lane);
+      op += c.hufHeaderSize;
+      if (c.nStreams == 4)
+        for (u32 k = 0; k < 3; k++) { ZRA_PUT(c.hufStreamSize[k]); ZRA_PUT(c.hufStreamSize[k] >> 8); }
+      for (u32 st = 0; st < c.nStreams; st++) {
+        warp_move(out + op, s.hufOut + (u64)st * s.hufStride, c.hufStreamSize[st], lane);
+        op += c.hufStreamSize[st];
+      }
+    } else {
+      const u32 type = litMode;  // 0 raw, 1 rle
+      if (n < 32) ZRA_PUT(type | (n << 3));
+      else if (n < 4096) { const u32 x = type | (1u << 2) | (n << 4); ZRA_PUT(x); ZRA_PUT(x >> 8); }
+      else { const u32 x = type | (3u << 2) | (n << 4); ZRA_PUT(x); ZRA_PUT(x >> 8); ZRA_PUT(x >> 16); }
+      if (type == 1) ZRA_PUT(s.lit[0]);
+      else { warp_move(out + op, s.lit, n, lane); op += n; }
+    }
+    warp_move(out + op, s.hdr + 256, c.seqHeaderSize, lane);
+    op += c.seqHeaderSize;
+    warp_move(out + op, s.seqOut, c.seqStreamSize, lane);
+    op += c.seqStreamSize;
+  }
+#undef ZRA_PUT
+  if (lane == 0) {
+    gc.outPos = op;
+    gc.litMode = litMode;
+    if (raw) { gc.rep[0] = c.repSave[0]; gc.rep[1] = c.repSave[1]; gc.rep[2] = c.repSave[2]; }
+  }
 }
 
 // XXH64 of the frame's input by four lanes (one accumulator each), then the final size.
@@ -213,6 +728,25 @@ size_t encode_scratch_bytes(u32 nFrames, u32 frameSize, u32 lastFrameLen, int le
   u32 ls = s1 > s2 ? s1 : s2, ll = l1 > l2 ? l1 : l2;
   lay->tabSEntries = 1u << ls;
   lay->tabLEntries = ll ? (1u << ll) : 1u;
+  // frames of at most 64 KiB take the frame-cooperative matcher (16-bit tables in shared memory)
+  {
+    // table logs of the shared-memory matcher: the level's own, unless overridden (tuning)
+    auto envu = [](const char* k, u32 d) { const char* e = getenv(k); return e ? (u32)strtoul(e, nullptr, 10) : d; };
+    int lv = level == 0 ? 3 : level;
+    u32 mlsTab[5] = {5, 6, 5, 5, 5};
+    lay->matchLogS = envu("ZRA_B200_ENC_LOGS", ls);
+    lay->matchLogL = envu("ZRA_B200_ENC_LOGL", ll);
+    lay->matchMls = envu("ZRA_B200_ENC_MLS", frameSize <= (16u << 10) ? (lv <= 1 ? 5u : 4u) : mlsTab[lv < 0 ? 0 : (lv > 4 ? 4 : lv)]);
+    if (lay->matchLogS > 16) lay->matchLogS = 16;
+    if (lay->matchLogL > 16) lay->matchLogL = 16;
+    if (lay->matchLogS < 8) lay->matchLogS = 8;
+    if (lay->matchLogL && lay->matchLogL < 8) lay->matchLogL = 8;
+  }
+  lay->matchSmem = 2u * ((1u << lay->matchLogS) + (lay->matchLogL ? (1u << lay->matchLogL) : 0u));
+  lay->matchThreads = lay->matchSmem > 100u * 1024u ? 512u : 256u;
+  if (getenv("ZRA_B200_ENC_THREADS")) lay->matchThreads = atoi(getenv("ZRA_B200_ENC_THREADS")) >= 512 ? 512u : 256u;
+  lay->matchSmem += 4u * lay->matchThreads + 4u * (256u + 128u);
+  lay->ctaMatch = frameSize <= 65536u && lay->matchSmem <= 226u * 1024u && !getenv("ZRA_B200_ENC_SERIAL");
   const u32 blk = frameSize < kBlockSizeMax ? frameSize : kBlockSizeMax;
   lay->seqStride = blk / 3 + 2;
   lay->litStride = (blk + 31u) & ~15u;
@@ -226,8 +760,8 @@ size_t encode_scratch_bytes(u32 nFrames, u32 frameSize, u32 lastFrameLen, int le
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return o; };
   const size_t n = nFrames;
   lay->offCtx = take(sizeof(EncCtx) * n);
-  lay->offTabS = take(4ull * lay->tabSEntries * n);
-  lay->offTabL = take(4ull * lay->tabLEntries * n);
+  lay->offTabS = take(lay->ctaMatch ? 16 : 4ull * lay->tabSEntries * n);
+  lay->offTabL = take(lay->ctaMatch ? 16 : 4ull * lay->tabLEntries * n);
   lay->offSeqs = take(8ull * lay->seqStride * n);
   lay->offLit = take((size_t)lay->litStride * n);
   lay->offHist = take(1024ull * n);
@@ -238,6 +772,7 @@ size_t encode_scratch_bytes(u32 nFrames, u32 frameSize, u32 lastFrameLen, int le
   lay->offStates = take(2ull * 1280 * n);
   lay->offSeqOut = take((size_t)lay->seqOutStride * n);
   lay->offCells = take(1024ull * n);
+  lay->offCnt = take(lay->ctaMatch ? 512ull * n : 16);
   lay->offOut = take((size_t)lay->outStride * n);
   lay->offSizes = take(4ull * n);
   lay->offOffsets = take(8ull * (n + 1));
@@ -251,21 +786,37 @@ u32 launch_encode_frames(const void* dIn, u64 inOff, u64 inEnd, u32 frameSize, u
   EncJob j{static_cast<const u8*>(dIn), inOff, inEnd, frameSize, nFrames, level, checksum ? 1u : 0u};
   EncView v{static_cast<u8*>(scratch), lay};
   u8* s = static_cast<u8*>(scratch);
-  // hash tables start empty for every frame
-  cudaMemsetAsync(s + lay.offTabS, 0, 4ull * lay.tabSEntries * nFrames, st);
-  cudaMemsetAsync(s + lay.offTabL, 0, 4ull * lay.tabLEntries * nFrames, st);
+  if (!lay.ctaMatch) {  // hash tables in HBM start empty for every frame
+    cudaMemsetAsync(s + lay.offTabS, 0, 4ull * lay.tabSEntries * nFrames, st);
+    cudaMemsetAsync(s + lay.offTabL, 0, 4ull * lay.tabLEntries * nFrames, st);
+  } else {
+    cudaFuncSetAttribute(k_enc_match_cta<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.matchSmem);
+    cudaFuncSetAttribute(k_enc_match_cta<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.matchSmem);
+  }
   const u32 tpb = 64;
+  static const bool serialEntropy = getenv("ZRA_B200_ENC_SERIAL_ENTROPY") != nullptr;  // thread-per-frame stages (debugging)
   u32 launches = 0;
   k_enc_begin<<<div_up(nFrames, 128), 128, 0, st>>>(j, v);
   launches++;
   for (u32 r = 0; r < lay.rounds; r++) {
-    k_enc_match<<<div_up(nFrames, tpb), tpb, 0, st>>>(j, v, r);
-    k_enc_literals<<<div_up(nFrames, tpb), tpb, 0, st>>>(j, v);
+    if (lay.ctaMatch) {
+      if (lay.matchThreads == 512) k_enc_match_cta<512><<<nFrames, 512, lay.matchSmem, st>>>(j, v);
+      else k_enc_match_cta<256><<<nFrames, 256, lay.matchSmem, st>>>(j, v);
+    } else {
+      k_enc_match<<<div_up(nFrames, tpb), tpb, 0, st>>>(j, v, r);
+      k_enc_literals<<<div_up(nFrames, tpb), tpb, 0, st>>>(j, v);
+      launches++;
+    }
     k_enc_plan<<<div_up(nFrames, tpb), tpb, 0, st>>>(j, v);
     k_enc_huf<<<div_up((u64)nFrames * 4, 128), 128, 0, st>>>(j, v);
-    k_enc_seq<<<div_up(nFrames, tpb), tpb, 0, st>>>(j, v);
-    k_enc_assemble<<<div_up(nFrames, tpb), tpb, 0, st>>>(j, v);
-    launches += 6;
+    if (serialEntropy) {
+      k_enc_seq<<<div_up(nFrames, tpb), tpb, 0, st>>>(j, v);
+      k_enc_assemble<<<div_up(nFrames, tpb), tpb, 0, st>>>(j, v);
+    } else {
+      k_enc_seq_warp<<<div_up(nFrames, kSeqEncWarps), kSeqEncWarps * 32, 0, st>>>(j, v);
+      k_enc_assemble_warp<<<div_up((u64)nFrames * 32, 256), 256, 0, st>>>(j, v);
+    }
+    launches += 5;
   }
   k_enc_finish<<<div_up((u64)nFrames * 4, 128), 128, 0, st>>>(j, v, reinterpret_cast<u32*>(s + lay.offSizes));
   return launches + 1;

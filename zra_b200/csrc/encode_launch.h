@@ -8,11 +8,13 @@ namespace zrab {
 
 // Per-batch device scratch of the encoder. Every frame in flight owns one slice of each region.
 struct EncodeLayout {
-  size_t offCtx, offTabS, offTabL, offSeqs, offLit, offHist, offCodes, offHuf, offHdr, offTT, offStates, offSeqOut, offCells,
+  size_t offCtx, offTabS, offTabL, offSeqs, offLit, offHist, offCodes, offHuf, offHdr, offTT, offStates, offSeqOut, offCells, offCnt,
       offOut, offSizes, offOffsets, offBlockSums;
   uint32_t tabSEntries, tabLEntries;  // per frame
   uint32_t seqStride, litStride, hufStride, seqOutStride, outStride;
   uint32_t rounds;                    // blocks per frame
+  uint32_t ctaMatch, matchSmem, matchThreads;  // frame-cooperative matcher (frames <= 64 KiB)
+  uint32_t matchLogS, matchLogL, matchMls;     // its table logs (16-bit entries) and short-hash width
 };
 
 // Scratch needed to encode `nFrames` frames of at most `frameSize` bytes at `level`.
