@@ -117,6 +117,32 @@ def measured_peak():
         return 6650.0, "fallback"
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of `kernel`, from the newest committed
+    `ncu --set full` summary under profiles/ (tools/summarise_profiles.py; tools/gpu_round.sh captures the bench
+    archive with ZRA_B200_CHUNKS=1, i.e. one launch = all frames, like the per-kernel timing pass). None if absent."""
+    import csv
+    import glob
+
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full_summary.csv")))
+    for f in reversed(files):
+        try:
+            rows = list(csv.reader(open(f)))
+            head = rows[0]
+            if kernel not in head:
+                continue
+            col = head.index(kernel)
+            tot = 0.0
+            for r in rows[1:]:
+                if r and r[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[r[1]]
+                    tot += float(r[col]) * scale
+            return int(tot), os.path.relpath(f, ROOT)
+        except Exception:
+            continue
+    return None, None
+
+
 # ---------------------------------------------------------------- CPU reference arm
 def cpu_reference(archive, data, threads, repeats=3):
     """The reference's CPU decompression of the SAME archive: best of `repeats`."""
@@ -444,6 +470,37 @@ def run_gpu(args):
     ms_max = float(t.item())
     value = world * size * args.steps / (ms_max / 1e3) / 1e9
 
+    # ---- N > 1: the final gather of configs[4] (every rank ends with the whole decoded archive), NCCL all-gather over
+    # NVLink / NVSwitch, timed separately from the decode (bounded by NVLink, reported on its own)
+    gather = None
+    if world > 1:
+        out_all = torch.empty(world * size, dtype=torch.uint8, device="cuda")
+        for _ in range(2):
+            dist.all_gather_into_tensor(out_all, d_out)
+        sums = torch.zeros(world, dtype=torch.int64, device="cuda")
+        sums[rank] = d_ref.sum(dtype=torch.int64)
+        dist.all_reduce(sums)
+        got = out_all.view(world, size).sum(dim=1, dtype=torch.int64)
+        assert torch.equal(got, sums), "gathered archive differs from the shards' originals"
+        assert torch.equal(out_all[rank * size:(rank + 1) * size], d_ref)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        gsteps = max(3, min(args.steps, 10))
+        barrier()
+        g0.record(stream)
+        for _ in range(gsteps):
+            dist.all_gather_into_tensor(out_all, d_out)
+        g1.record(stream)
+        barrier()
+        tg = torch.tensor([g0.elapsed_time(g1) / gsteps], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        gms = float(tg.item())
+        gather = {"op": "ncclAllGather of the decoded shards (every GPU ends with the whole archive)", "ms": round(gms, 4),
+                  "bytes_in_per_gpu": int((world - 1) * size), "GBps_in_per_gpu": round((world - 1) * size / gms / 1e6, 2),
+                  "nvlink_peak_GBps_per_direction": 900.0,
+                  "decode_then_gather_GBps": round(world * size / ((ms_max / args.steps + gms) / 1e3) / 1e9, 3)}
+        del out_all
+        torch.cuda.empty_cache()
+
     # ---- per-kernel breakdown (separate pass with an event after every launch)
     ctx.set_profiling(True)
     for _ in range(args.steps):
@@ -457,9 +514,14 @@ def run_gpu(args):
     peak, peak_kind = measured_peak()
     alg_bytes = archive.size + size
     top_ms = kernels[top]["ms_per_step"]
+    traffic, traffic_src = ncu_traffic(top)
+    top_launches = max(1.0, kernels[top]["launches_per_step"])
     roofline = {
         "bound": "hbm", "kernel": top, "achieved": round(alg_bytes / (top_ms / 1e3) / 1e9, 2), "peak": peak, "peak_kind": peak_kind,
-        "unit": "GB/s", "frac": round(alg_bytes / (top_ms / 1e3) / 1e9 / peak, 5), "traffic": None,
+        "unit": "GB/s", "frac": round(alg_bytes / (top_ms / 1e3) / 1e9 / peak, 5), "traffic": traffic,
+        "traffic_note": (f"DRAM read+write bytes of ONE launch of {top} from {traffic_src} (ncu --set full on the same archive with "
+                         "ZRA_B200_CHUNKS=1: one launch = all frames, the geometry of this timing pass)") if traffic else None,
+        "launches_per_step": top_launches,
         "algorithmic_bytes_per_step": int(alg_bytes), "kernel_ms_per_step": round(top_ms, 4),
         "kernel_share_of_step": round(top_ms / total_kernel_ms, 4),
         "whole_step": {"achieved": round(alg_bytes / (ms_max / args.steps / 1e3) / 1e9, 2),
@@ -526,6 +588,8 @@ def run_gpu(args):
             "gpu_launches": int(launches),
             "roofline": roofline,
         }
+        if gather is not None:
+            line["gather"] = gather
         if ra is not None:
             line["random_access"] = ra
         if comp is not None:

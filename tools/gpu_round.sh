@@ -11,6 +11,6 @@ cat gpurun_out/${tag}_bench.json
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${tag}_bench_ref.json 2>> gpurun_out/${tag}_bench.err; cat gpurun_out/${tag}_bench_ref.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-ra > gpurun_out/${tag}_ncu_bench.log 2>&1; echo "ncu launches rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_(block_setup|huf_decode|seq_decode|seq_execute|frame_finish)' -c 5 \
-    -f -o gpurun_out/${tag}_full python tools/profile_decode.py 256 65536 1 > gpurun_out/${tag}_ncu_full.log 2>&1; echo "ncu full rc=$?"
+ZRA_B200_CHUNKS=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_(block_setup|huf_decode|seq_decode|seq_execute|frame_finish)' -c 5 \
+    -f -o gpurun_out/${tag}_full python tools/profile_decode.py 1024 65536 1 > gpurun_out/${tag}_ncu_full.log 2>&1; echo "ncu full rc=$?"
 ls -la gpurun_out

@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(32) k_huf_decode(const u8* __restrict__ src, c
           i = 0;
           laneDone = false;
           if (!br.init(src, descs[f].srcOff + c.strOff[s], c.strLen[s], ring, 32)) {
-            atomicCAS(&ctxs[f].status, 0u, (u32)ZE_CORRUPTION);
+            ctxs[f].status = (u32)ZE_CORRUPTION;  // literals fail first in the reference: this code wins over the sequence stage's
             laneDone = true;
           } else {
             // head: bring the output cursor to a 4-byte boundary so that the groups store whole words
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(32) k_huf_decode(const u8* __restrict__ src, c
           br.p -= (i32)(e >> 8);
         }
         laneDone = true;
-        if (br.p != br.b0) atomicCAS(&ctxs[frame].status, 0u, (u32)ZE_CORRUPTION);
+        if (br.p != br.b0) ctxs[frame].status = (u32)ZE_CORRUPTION;
       }
     }
     __syncwarp();
@@ -208,11 +208,14 @@ __global__ void __launch_bounds__(32) k_huf_decode(const u8* __restrict__ src, c
 // completion test. A lane that finishes its frame pulls the next one from the work list and the
 // warp copies that frame's tables in cooperatively.
 constexpr u32 kSeqSlotEntries = 1280;  // ll 512 + ml 512 + of 256
-constexpr u32 kSeqSlots = 88;          // frames resident per CTA: 88 x 2560 B + LUTs = 220.5 KiB of the SM's 227 KiB
-constexpr u32 kSeqThreads = 96;        // three warps; lanes 88..95 idle
-constexpr u32 kSeqWarpSmem = kSeqSlots * kSeqSlotEntries * sizeof(CSym) + 128 * sizeof(u32) + kRingWords * kSeqThreads * sizeof(u32);
-static_assert(kSeqWarpSmem <= 227 * 1024, "k_seq_decode shared memory");
+constexpr u32 kSeqSlotsMax = 88;       // frames resident per CTA: 88 x 2560 B + LUTs = 220.5 KiB of the SM's 227 KiB
+constexpr u32 kSeqThreads = 96;        // three warps; lanes >= kSeqSlots idle
+constexpr u32 seq_smem_bytes(u32 slots) { return slots * kSeqSlotEntries * sizeof(CSym) + 128 * sizeof(u32) + kRingWords * kSeqThreads * sizeof(u32); }
+static_assert(seq_smem_bytes(kSeqSlotsMax) <= 227 * 1024, "k_seq_decode shared memory");
 
+// kSeqSlots: 88 fills the SM; 78 / 72 / 64 leave room for 2 / 3 / 5 Huffman warps (k_huf_decode, 10 KiB + 1 KiB
+// reserved each) to be resident beside it when that stage runs on the side stream.
+template <u32 kSeqSlots>
 __global__ void __launch_bounds__(kSeqThreads) k_seq_decode(const u8* __restrict__ src, const FrameDesc* __restrict__ descs,
                                                    FrameCtx* __restrict__ ctxs, const FrameTables* __restrict__ tabs,
                                                    u64* __restrict__ seqs, u32 seqStride, RoundWork* __restrict__ work,
@@ -427,9 +430,13 @@ constexpr u32 kTileBytes = 4096;
 constexpr u32 kTileStride = kTileBytes + 32;
 constexpr u32 kShortMax = 64;  // sequences with ll and ml below this go through the tile
 
-__global__ void __launch_bounds__(kExecWarps * 32, 4) k_seq_execute(const u8* __restrict__ src, u8* dst, const FrameDesc* __restrict__ descs,
+enum ExecFlags : u32 { XF_PF_LIT = 1, XF_PF_MATCH = 2 };
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+template <int MINB>
+__global__ void __launch_bounds__(kExecWarps * 32, MINB) k_seq_execute(const u8* __restrict__ src, u8* dst, const FrameDesc* __restrict__ descs,
                                                      const FrameCtx* __restrict__ ctxs, const u8* __restrict__ lit, u32 litStride,
-                                                     const u64* __restrict__ seqs, u32 seqStride, u32 nFrames) {
+                                                     const u64* __restrict__ seqs, u32 seqStride, u32 nFrames, u32 xflags) {
   __shared__ __align__(16) u8 tiles[kExecWarps][kTileStride];
   u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   u32 lane = threadIdx.x & 31;
@@ -472,6 +479,23 @@ __global__ void __launch_bounds__(kExecWarps * 32, 4) k_seq_execute(const u8* __
     if (lane == 0) p = carry;
     const u32 S0 = rec_out_end(carry);  // block-relative start of this group's output
     carry = shfl64(s, 31);
+    if (xflags && base + 32 < nbSeq) {
+      // the next group's inputs are requested into L1 a whole iteration ahead: its literals (contiguous in the
+      // literal buffer, from this group's literal end) and every lane's match source (earlier output of this
+      // frame, normally an L2 hit); a line that this group still writes is simply updated by the stores
+      if ((xflags & XF_PF_LIT) && !rle && lane < 2) {
+        const u32 at = rec_lit_end(carry) + 128u * lane;
+        if (at < c.litSize) prefetch_l1(litp + at);
+      }
+      if (xflags & XF_PF_MATCH) {
+        u64 pn = shfl64_up1(sNext);
+        if (lane == 0) pn = carry;
+        const u32 lln = rec_lit_end(sNext) - rec_lit_end(pn);
+        const u32 mposn = rec_out_end(pn) + lln;
+        const u32 offn = rec_off(sNext);
+        if (rec_out_end(sNext) > mposn && offn <= blkDst + mposn) prefetch_l1(blk + mposn - offn);
+      }
+    }
     const u32 S = rec_out_end(carry) - S0;
     const u32 pl = rec_lit_end(p), po = rec_out_end(p);
     const u32 ll = rec_lit_end(s) - pl;
@@ -699,6 +723,14 @@ void KernelTimer::collect() {
   }
   used_ = 0;
 }
+void KernelTimer::dump_timeline(FILE* f) {
+  for (size_t i = 0; i < used_; i++) {
+    float t = -1;
+    cudaEventSynchronize(marks_[i].ev);
+    cudaEventElapsedTime(&t, marks_[0].ev, marks_[i].ev);
+    fprintf(f, "TL %zu %s %.4f\n", i, kernel_name(marks_[i].id), t);
+  }
+}
 #define ZRA_MARK(id) do { if (timer) timer->mark(id, st); } while (0)
 
 static int sm_count() {
@@ -711,9 +743,19 @@ static int sm_count() {
   return n;
 }
 
+static u32 env_u32(const char* name, u32 dflt) {
+  const char* s = getenv(name);
+  return s ? (u32)strtoul(s, nullptr, 10) : dflt;
+}
+static u32 exec_flags() { static u32 v = env_u32("ZRA_B200_EXEC_FLAGS", 0); return v; }
+static u32 exec_occupancy() { static u32 v = env_u32("ZRA_B200_EXEC_OCC", 4); return v; }
+
 static void configure_kernels() {
   // per device; cheap enough to repeat on every launch sequence
-  cudaFuncSetAttribute(k_seq_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSeqWarpSmem);
+  cudaFuncSetAttribute(k_seq_decode<88>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem_bytes(88));
+  cudaFuncSetAttribute(k_seq_decode<78>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem_bytes(78));
+  cudaFuncSetAttribute(k_seq_decode<72>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem_bytes(72));
+  cudaFuncSetAttribute(k_seq_decode<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem_bytes(64));
   cudaFuncSetAttribute(k_huf_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHufWarpSmem);
 }
 
@@ -756,7 +798,7 @@ void launch_summary_reset(void* scratch, const DecodeLayout& lay, cudaStream_t s
 }
 
 void launch_decode_rounds(const void* src, void* dst, u32 nFrames, u32 rounds, bool first, void* scratch, const DecodeLayout& lay,
-                          cudaStream_t st, KernelTimer* timer) {
+                          cudaStream_t st, KernelTimer* timer, const SideLane* side) {
   if (!nFrames) return;
   configure_kernels();
   u8* s = static_cast<u8*>(scratch);
@@ -772,19 +814,43 @@ void launch_decode_rounds(const void* src, void* dst, u32 nFrames, u32 rounds, b
   const u32 sms = (u32)sm_count();
   // persistent grids: as many warps as fit the SMs' shared memory, never more than there is work
   const u32 hufWarps = sms * 20 < div_up(nFrames, 8) ? sms * 20 : div_up(nFrames, 8);
-  const u32 seqCtas = sms < div_up(nFrames, kSeqSlots) ? sms : div_up(nFrames, kSeqSlots);
+  static const u32 forkHuf = env_u32("ZRA_B200_FORK_HUF", 0);
+  if (timer || !forkHuf) side = nullptr;  // per-kernel timing wants one stream
+  static const u32 slotsEnv = env_u32("ZRA_B200_SEQ_SLOTS", 0);
+  const u32 slots = slotsEnv == 64 || slotsEnv == 72 || slotsEnv == 78 || slotsEnv == 88 ? slotsEnv : (side ? 72u : 88u);
+  const u32 seqCtas = sms < div_up(nFrames, slots) ? sms : div_up(nFrames, slots);
   for (u32 r = 0; r < rounds; r++) {
     cudaMemsetAsync(work, 0, sizeof(RoundWork), st);
     ZRA_MARK(K_START);
     k_block_setup<<<div_up(nFrames, 64), 64, 0, st>>>(in, descs, ctxs, tabs, nFrames, (first && r == 0) ? 1u : 0u, work, hufList,
                                                       seqList);
     ZRA_MARK(K_BLOCK_SETUP);
-    k_huf_decode<<<hufWarps, 32, kHufWarpSmem, st>>>(in, descs, ctxs, tabs, lit, lay.litStride, work, hufList);
-    ZRA_MARK(K_HUF_DECODE);
-    k_seq_decode<<<seqCtas, kSeqThreads, kSeqWarpSmem, st>>>(in, descs, ctxs, tabs, seqs, lay.seqStride, work, seqList);
+    // the sequence stage goes first so that its whole-SM CTAs are placed before the Huffman warps fill the rest
+    cudaStream_t hs = st;
+    if (side) {
+      cudaEventRecord(side->setupDone, st);
+      hs = side->st;
+    } else {
+      k_huf_decode<<<hufWarps, 32, kHufWarpSmem, st>>>(in, descs, ctxs, tabs, lit, lay.litStride, work, hufList);
+      ZRA_MARK(K_HUF_DECODE);
+    }
+    if (slots == 88) k_seq_decode<88><<<seqCtas, kSeqThreads, seq_smem_bytes(88), st>>>(in, descs, ctxs, tabs, seqs, lay.seqStride, work, seqList);
+    else if (slots == 78) k_seq_decode<78><<<seqCtas, kSeqThreads, seq_smem_bytes(78), st>>>(in, descs, ctxs, tabs, seqs, lay.seqStride, work, seqList);
+    else if (slots == 72) k_seq_decode<72><<<seqCtas, kSeqThreads, seq_smem_bytes(72), st>>>(in, descs, ctxs, tabs, seqs, lay.seqStride, work, seqList);
+    else k_seq_decode<64><<<seqCtas, kSeqThreads, seq_smem_bytes(64), st>>>(in, descs, ctxs, tabs, seqs, lay.seqStride, work, seqList);
     ZRA_MARK(K_SEQ_DECODE);
-    k_seq_execute<<<div_up((u64)nFrames * 32, kExecWarps * 32), kExecWarps * 32, 0, st>>>(in, static_cast<u8*>(dst), descs, ctxs, lit, lay.litStride, seqs,
-                                                                 lay.seqStride, nFrames);
+    if (side) {
+      cudaStreamWaitEvent(hs, side->setupDone, 0);
+      k_huf_decode<<<hufWarps, 32, kHufWarpSmem, hs>>>(in, descs, ctxs, tabs, lit, lay.litStride, work, hufList);
+      cudaEventRecord(side->hufDone, hs);
+      cudaStreamWaitEvent(st, side->hufDone, 0);
+    }
+    if (exec_occupancy() >= 5)
+      k_seq_execute<5><<<div_up((u64)nFrames * 32, kExecWarps * 32), kExecWarps * 32, 0, st>>>(in, static_cast<u8*>(dst), descs, ctxs, lit, lay.litStride,
+                                                                      seqs, lay.seqStride, nFrames, exec_flags());
+    else
+      k_seq_execute<4><<<div_up((u64)nFrames * 32, kExecWarps * 32), kExecWarps * 32, 0, st>>>(in, static_cast<u8*>(dst), descs, ctxs, lit, lay.litStride,
+                                                                      seqs, lay.seqStride, nFrames, exec_flags());
     ZRA_MARK(K_SEQ_EXECUTE);
   }
 }

@@ -1,5 +1,6 @@
 // decode_launch.h — host-visible launch interface of decode_kernels.cu (internal to the library).
 #pragma once
+#include <cstdio>
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
@@ -18,6 +19,7 @@ class KernelTimer {
   void mark(int id, cudaStream_t st);   // records an event tagged with the kernel just launched
   void collect();                       // call after a stream synchronize; folds the marks into totals
   void reset();
+  void dump_timeline(FILE* f);            // every mark's time relative to the first one (tuning aid, ZRA_B200_TIMELINE=1)
   double ms[K_COUNT] = {};
   uint64_t launches[K_COUNT] = {};
 
@@ -48,9 +50,16 @@ void launch_build_descs(const void* archive, uint64_t tableOff, uint64_t headerS
                         uint64_t uncompressedSize, uint32_t frameSize, uint32_t firstFrame, uint32_t nFrames, uint64_t dstBase,
                         void* scratch, const DecodeLayout& lay, cudaStream_t st, KernelTimer* timer = nullptr);
 
+// A second stream and two events of the caller's: with them the Huffman literal stage of a round runs BESIDE the
+// sequence stage (both only depend on the setup kernel) instead of before it.
+struct SideLane {
+  cudaStream_t st;
+  cudaEvent_t setupDone, hufDone;
+};
+
 // Runs `rounds` rounds (one block of every frame per round). `first` resets the frame contexts.
 void launch_decode_rounds(const void* src, void* dst, uint32_t nFrames, uint32_t rounds, bool first, void* scratch,
-                          const DecodeLayout& lay, cudaStream_t st, KernelTimer* timer = nullptr);
+                          const DecodeLayout& lay, cudaStream_t st, KernelTimer* timer = nullptr, const SideLane* side = nullptr);
 
 // Checksums + final checks + summary. May be called again after extra rounds.
 void launch_frame_finish(const void* src, const void* dst, uint32_t nFrames, void* scratch, const DecodeLayout& lay,

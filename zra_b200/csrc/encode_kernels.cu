@@ -734,8 +734,16 @@ size_t encode_scratch_bytes(u32 nFrames, u32 frameSize, u32 lastFrameLen, int le
     auto envu = [](const char* k, u32 d) { const char* e = getenv(k); return e ? (u32)strtoul(e, nullptr, 10) : d; };
     int lv = level == 0 ? 3 : level;
     u32 mlsTab[5] = {5, 6, 5, 5, 5};
-    lay->matchLogS = envu("ZRA_B200_ENC_LOGS", ls);
-    lay->matchLogL = envu("ZRA_B200_ENC_LOGL", ll);
+    // The double-fast levels run with tables a quarter of the reference's size: the matcher inserts EVERY position
+    // (the serial reference only the ones it visits), so the smaller tables still find as much, and the number of
+    // frames resident per SM (= shared memory per CTA) is what sets the speed. Measured on the bench data, 64 KiB
+    // frames, level 3 (profiles/r01g): logs 15/16 -> 4.8 GB/s, archive -0.65 % vs the reference's; 13/14 -> 13.7 GB/s,
+    // +0.81 % (text); mixed +0.20 %. The 3 % ratio bound of north_star holds with margin.
+    u32 dS = ls, dL = ll;
+    if (ll) { dS = ls > 12 ? ls - 2 : (ls > 10 ? 10 : ls); dL = ll > 12 ? ll - 2 : (ll > 10 ? 10 : ll); }
+    else if (ls > 13) dS = ls - 1;  // fast levels, big tables: level 2 / 64 KiB 15 -> 14: 10.7 -> 17.9 GB/s, archive -0.36 % -> +0.67 %
+    lay->matchLogS = envu("ZRA_B200_ENC_LOGS", dS);
+    lay->matchLogL = envu("ZRA_B200_ENC_LOGL", dL);
     lay->matchMls = envu("ZRA_B200_ENC_MLS", frameSize <= (16u << 10) ? (lv <= 1 ? 5u : 4u) : mlsTab[lv < 0 ? 0 : (lv > 4 ? 4 : lv)]);
     if (lay->matchLogS > 16) lay->matchLogS = 16;
     if (lay->matchLogL > 16) lay->matchLogL = 16;

@@ -24,8 +24,20 @@ GpuContext::GpuContext(int device) {
   device_ = device;
   if (check(cudaSetDevice(device_), "cudaSetDevice")) return;
   if (check(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), "cudaStreamCreate")) return;
-  for (auto& s : pool_)
-    if (check(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate")) return;
+  {
+    // chunk i runs on pool_[i]: earlier chunks get the higher priority, so that the tail kernels of an early chunk
+    // (whose output the host is waiting to download) are not queued behind a later chunk's whole-SM CTAs
+    int least = 0, greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&least, &greatest);
+    static const bool flat = getenv("ZRA_B200_FLAT_PRIORITY") != nullptr;
+    for (int i = 0; i < kPoolStreams; i++) {
+      int prio = flat ? least : std::min(least, greatest + i);
+      if (check(cudaStreamCreateWithPriority(&pool_[i], cudaStreamNonBlocking, prio), "cudaStreamCreate")) return;
+      if (check(cudaStreamCreateWithPriority(&side_[i].st, cudaStreamNonBlocking, prio), "cudaStreamCreate")) return;
+      if (check(cudaEventCreateWithFlags(&side_[i].setupDone, cudaEventDisableTiming), "cudaEventCreate")) return;
+      if (check(cudaEventCreateWithFlags(&side_[i].hufDone, cudaEventDisableTiming), "cudaEventCreate")) return;
+    }
+  }
   if (check(cudaEventCreateWithFlags(&forkEvent_, cudaEventDisableTiming), "cudaEventCreate")) return;
   if (check(cudaMallocHost(&summaryHost_, sizeof(uint32_t) * 4 * kMaxChunks), "cudaMallocHost")) return;
   ok_ = true;
@@ -39,6 +51,11 @@ GpuContext::~GpuContext() {
     if (b->p) cudaFree(b->p);
   for (auto& s : pool_)
     if (s) cudaStreamDestroy(s);
+  for (auto& l : side_) {
+    if (l.st) cudaStreamDestroy(l.st);
+    if (l.setupDone) cudaEventDestroy(l.setupDone);
+    if (l.hufDone) cudaEventDestroy(l.hufDone);
+  }
   if (forkEvent_) cudaEventDestroy(forkEvent_);
   if (summaryHost_) cudaFreeHost(summaryHost_);
   if (stream_) cudaStreamDestroy(stream_);
@@ -92,6 +109,17 @@ static uint32_t chunk_target() {
   return v;
 }
 
+// Host-pointer calls (uploads and downloads inside the chunk pipeline) are PCIe-bound: the time before the
+// first download can start is one chunk's upload + decode, so they are cut finer than device-resident calls.
+static uint32_t io_chunk_target() {
+  static uint32_t v = [] {
+    const char* s = getenv("ZRA_B200_IO_CHUNKS");
+    uint32_t n = s ? (uint32_t)strtoul(s, nullptr, 10) : 4;  // measured (profiles/r01e): 4 -> 42.7 GB/s, 8 -> 42.4, 16 -> 38.4, 32 -> 32.9
+    return std::max<uint32_t>(1, std::min<uint32_t>(n, 256));
+  }();
+  return v;
+}
+
 namespace {
   struct Chunk {
     uint64_t f0;
@@ -99,6 +127,7 @@ namespace {
     DecodeLayout lay;
     uint8_t* scratch;
     cudaStream_t st;
+    const SideLane* side;
     uint32_t* summary;  // pinned host words
   };
 }  // namespace
@@ -114,7 +143,8 @@ DecodeResult GpuContext::decode(const void* dSrc, size_t srcSize, const HostFram
   // frames per group = what the scratch budget holds; a group is cut into chunks that run concurrently
   const uint64_t groupFrames = std::min<uint64_t>(std::max<uint64_t>(1, scratch_budget() / perFrame), 1u << 22);
   const uint32_t baseRounds = std::max<uint32_t>(1, (maxDstCap + (1u << 17) - 1) >> 17);
-  const bool single = profiling_;  // per-kernel event timing needs one chunk on one stream
+  static const bool timeline = getenv("ZRA_B200_TIMELINE") != nullptr;  // tuning aid: keep the chunk pipeline, dump every mark
+  const bool single = profiling_ && !timeline;  // per-kernel event timing needs one chunk on one stream
   KernelTimer* tm = profiling_ ? &timer : nullptr;
   std::vector<uint8_t> ctxHost;
   std::vector<Chunk> chunks;
@@ -123,17 +153,43 @@ DecodeResult GpuContext::decode(const void* dSrc, size_t srcSize, const HostFram
   for (uint64_t g0 = 0; g0 < nFrames; g0 += groupFrames) {
     const uint64_t gN = std::min<uint64_t>(groupFrames, nFrames - g0);
     // ---- plan the chunks of this group
-    uint32_t nChunks = single ? 1u : (uint32_t)std::min<uint64_t>(chunk_target(), std::max<uint64_t>(1, gN / 64));
+    const bool hostIo = io && (io->hostSrc || io->hostDst);
+    uint32_t nChunks = single ? 1u : (uint32_t)std::min<uint64_t>(hostIo ? io_chunk_target() : chunk_target(), std::max<uint64_t>(1, gN / 64));
     nChunks = std::min<uint32_t>(nChunks, kMaxChunks);
     const uint64_t per = (gN + nChunks - 1) / nChunks;
     chunks.clear();
     size_t total = 0;
-    for (uint64_t c0 = 0; c0 < gN; c0 += per) {
+    auto add_chunk = [&](uint64_t c0, uint64_t n) {
       Chunk c;
       c.f0 = g0 + c0;
-      c.n = (uint32_t)std::min<uint64_t>(per, gN - c0);
+      c.n = (uint32_t)n;
       total += decode_scratch_bytes(c.n, maxDstCap, &c.lay);
       chunks.push_back(c);
+    };
+    // tuning aids: explicit chunk sizes "a,b,c" (the rest = one more chunk) for device-resident / host-pointer calls
+    static const char* planEnv = getenv("ZRA_B200_PLAN");
+    static const char* ioPlanEnv = getenv("ZRA_B200_IO_PLAN");
+    const char* plan = hostIo ? ioPlanEnv : planEnv;
+    if (plan && !single) {
+      uint64_t c0 = 0;
+      for (const char* q = plan; *q && c0 < gN;) {
+        uint64_t n = std::min<uint64_t>(strtoull(q, const_cast<char**>(&q), 10), gN - c0);
+        if (n) add_chunk(c0, n);
+        c0 += n;
+        if (*q == ',') q++; else break;
+      }
+      if (c0 < gN) add_chunk(c0, gN - c0);
+    } else if (hostIo && !single && gN >= 2048 && getenv("ZRA_B200_IO_GEOMETRIC")) {
+      // host-pointer calls are PCIe-bound and every chunk's kernels take about the same time whatever its size
+      // (serial per-frame chains), so the first download can only start one upload + one kernel latency into the
+      // call: a small first chunk starts it early, and the sizes grow geometrically so that each later chunk
+      // is decoded by the time the downloads before it have drained (1/32, 1/16, 1/8, 1/4, 1/4, rest).
+      const uint64_t cut[5] = {gN / 32, gN / 16, gN / 8, gN / 4, gN / 4};
+      uint64_t c0 = 0;
+      for (uint64_t n : cut) { add_chunk(c0, n); c0 += n; }
+      add_chunk(c0, gN - c0);
+    } else {
+      for (uint64_t c0 = 0; c0 < gN; c0 += per) add_chunk(c0, std::min<uint64_t>(per, gN - c0));
     }
     uint8_t* base = static_cast<uint8_t*>(ensure(scratch, total));
     if (!base) return fail_cuda();
@@ -143,6 +199,8 @@ DecodeResult GpuContext::decode(const void* dSrc, size_t srcSize, const HostFram
       chunks[i].scratch = base + off;
       off += decode_scratch_bytes(chunks[i].n, maxDstCap, &tmp);
       chunks[i].st = single ? st : pool_[i % kPoolStreams];
+      // the side lane's events are per pool stream: only the first kPoolStreams chunks (one per stream) fork
+      chunks[i].side = (single || i >= (size_t)kPoolStreams) ? nullptr : &side_[i];
       chunks[i].summary = summaryHost_ + 4 * i;
     }
     // ---- fork: the pool streams start after whatever the caller queued on `st`
@@ -190,13 +248,17 @@ DecodeResult GpuContext::decode(const void* dSrc, size_t srcSize, const HostFram
                            (uint32_t)(firstFrame + c.f0), c.n, firstFrame * info->frameSize, c.scratch, c.lay, c.st, tm);
         launches_ += 1;
       }
-      launch_decode_rounds(dSrc, dDst, c.n, baseRounds, true, c.scratch, c.lay, c.st, tm);
+      launch_decode_rounds(dSrc, dDst, c.n, baseRounds, true, c.scratch, c.lay, c.st, tm, c.side);
       launches_ += 4ull * baseRounds;
       if (!enqueue_tail(c)) return fail_cuda();
     }
     for (Chunk& c : chunks)
       if (!enqueue_download(c)) return fail_cuda();
     // ---- join, then look at every chunk's summary (in frame order, so the lowest failing frame wins)
+    if (tm && timeline) {
+      for (Chunk& c : chunks) cudaStreamSynchronize(c.st);
+      tm->dump_timeline(stderr);
+    }
     for (Chunk& c : chunks) {
       if (check(cudaStreamSynchronize(c.st), "decode kernels")) return fail_cuda();
       if (tm) tm->collect();
