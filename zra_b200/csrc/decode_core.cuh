@@ -135,8 +135,18 @@ ZRA_DEV u32 setup_seq_table(CSym* table, u32* logOut, u32 type, u32 kind, const 
 }
 
 // ---------------------------------------------------------------- block_setup (1 thread / frame)
-ZRA_DEV void block_setup(const u8* srcBase, const FrameDesc& d, FrameCtx& c, FrameTables& t, bool firstRound) {
+// Where block_setup builds the three sequence tables: straight into the frame's FrameTables (stage == nullptr), or
+// into a caller-provided staging area (the kernel: shared memory; `built` then tells which tables were rebuilt
+// this round and must be copied out — a "repeat" table keeps the previous block's copy in FrameTables).
+struct SeqTableStage {
+  CSym *ll, *ml, *of;
+  u32 built;  // bit 0: ll, bit 1: ml, bit 2: of
+};
+
+ZRA_DEV void block_setup(const u8* srcBase, const FrameDesc& d, FrameCtx& c, FrameTables& t, bool firstRound,
+                         SeqTableStage* stage = nullptr) {
   const u8* f = srcBase + d.srcOff;
+  if (stage) stage->built = 0;
   if (firstRound) { if (!parse_frame_header(f, d, c)) return; }
   c.blkType = BT_NONE;
   if (c.status || (c.flags & FF_DONE)) return;
@@ -246,15 +256,16 @@ ZRA_DEV void block_setup(const u8* srcBase, const FrameDesc& d, FrameCtx& c, Fra
     if (ip + 1 > iend) { frame_fail(c, ZE_SRC_WRONG); return; }
     u32 modes = *ip++;
     bool rep = (c.flags & FF_FSE_VALID) != 0;
-    u32 h = setup_seq_table(t.ll, &c.llLog, modes >> 6, SEQ_LL, ip, (u32)(iend - ip), rep);
+    u32 h = setup_seq_table(stage ? stage->ll : t.ll, &c.llLog, modes >> 6, SEQ_LL, ip, (u32)(iend - ip), rep);
     if (h == 0xFFFFFFFFu) { frame_fail(c, ZE_CORRUPTION); return; }
     ip += h;
-    h = setup_seq_table(t.of, &c.ofLog, (modes >> 4) & 3, SEQ_OF, ip, (u32)(iend - ip), rep);
+    h = setup_seq_table(stage ? stage->of : t.of, &c.ofLog, (modes >> 4) & 3, SEQ_OF, ip, (u32)(iend - ip), rep);
     if (h == 0xFFFFFFFFu) { frame_fail(c, ZE_CORRUPTION); return; }
     ip += h;
-    h = setup_seq_table(t.ml, &c.mlLog, (modes >> 2) & 3, SEQ_ML, ip, (u32)(iend - ip), rep);
+    h = setup_seq_table(stage ? stage->ml : t.ml, &c.mlLog, (modes >> 2) & 3, SEQ_ML, ip, (u32)(iend - ip), rep);
     if (h == 0xFFFFFFFFu) { frame_fail(c, ZE_CORRUPTION); return; }
     ip += h;
+    if (stage) stage->built = ((modes >> 6) != 3 ? 1u : 0u) | (((modes >> 2) & 3) != 3 ? 2u : 0u) | (((modes >> 4) & 3) != 3 ? 4u : 0u);
     c.flags |= FF_FSE_VALID;
     if (ip >= iend) { frame_fail(c, ZE_CORRUPTION); return; }  // the bitstream needs at least its end mark
   }

@@ -62,17 +62,50 @@ __global__ void k_build_descs(const u8* __restrict__ archive, u64 tableOff, u64 
   descs[i] = d;
 }
 
-__global__ void k_block_setup(const u8* __restrict__ src, const FrameDesc* __restrict__ descs, FrameCtx* __restrict__ ctxs,
-                              FrameTables* __restrict__ tabs, u32 nFrames, u32 firstRound, RoundWork* __restrict__ work,
-                              u32* __restrict__ hufList, u32* __restrict__ seqList) {
-  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nFrames) return;
-  FrameCtx c = ctxs[i];
-  block_setup(src, descs[i], c, tabs[i], firstRound != 0);
-  ctxs[i] = c;
-  if (c.blkType == BT_COMPRESSED && !c.status) {
-    if (c.litMode == LIT_HUF && c.litSize) hufList[atomicAdd(&work->hufCount, 1u)] = i;
-    if (c.nbSeq) seqList[atomicAdd(&work->seqCount, 1u)] = i;
+// One warp per CTA, one frame per lane. The three sequence tables are BUILT IN SHARED MEMORY (the build is a
+// read-modify-write of every cell: spread the symbols, then number the cells; in HBM scratch each of those 2 x 1280
+// dependent accesses is an L2 round trip) and leave with coalesced word stores by the whole warp. Every lane's
+// staging area is padded by one word so that lanes touching the same cell index fall into different banks.
+constexpr u32 kSeqSlotEntries = 1280;  // ll 512 + ml 512 + of 256 (the sequence tables of one frame)
+constexpr u32 kSetupStageWords = kSeqSlotEntries * sizeof(CSym) / 4 + 1;  // 641
+constexpr u32 kSetupSmem = 32 * kSetupStageWords * 4;                      // 80.1 KiB
+
+__global__ void __launch_bounds__(32) k_block_setup(const u8* __restrict__ src, const FrameDesc* __restrict__ descs,
+                                                    FrameCtx* __restrict__ ctxs, FrameTables* __restrict__ tabs, u32 nFrames,
+                                                    u32 firstRound, RoundWork* __restrict__ work, u32* __restrict__ hufList,
+                                                    u32* __restrict__ seqList) {
+  extern __shared__ __align__(16) u8 smem[];
+  u32* stageWords = reinterpret_cast<u32*>(smem);
+  const u32 lane = threadIdx.x;
+  const u32 i = blockIdx.x * 32 + lane;
+  SeqTableStage stage;
+  stage.ll = reinterpret_cast<CSym*>(stageWords + lane * kSetupStageWords);
+  stage.ml = stage.ll + 512;
+  stage.of = stage.ll + 1024;
+  stage.built = 0;
+  if (i < nFrames) {
+    FrameCtx c = ctxs[i];
+    block_setup(src, descs[i], c, tabs[i], firstRound != 0, &stage);
+    ctxs[i] = c;
+    if (c.blkType == BT_COMPRESSED && !c.status) {
+      if (c.litMode == LIT_HUF && c.litSize) hufList[atomicAdd(&work->hufCount, 1u)] = i;
+      if (c.nbSeq) seqList[atomicAdd(&work->seqCount, 1u)] = i;
+    } else {
+      stage.built = 0;  // nothing will read the tables of a failed / raw / RLE block
+    }
+  }
+  __syncwarp();
+  // copy-out: lane by lane, the whole warp moves the tables that lane rebuilt (ll 256 words | ml 256 | of 128)
+  u32 any = __ballot_sync(kFull, stage.built != 0);
+  while (any) {
+    const int who = __ffs(any) - 1;
+    any &= any - 1;
+    const u32 built = __shfl_sync(kFull, stage.built, who);
+    const u32* from = stageWords + who * kSetupStageWords;
+    u32* to = reinterpret_cast<u32*>(&tabs[blockIdx.x * 32 + who]);
+    if (built & 1u) for (u32 k = lane; k < 256; k += 32) to[k] = from[k];
+    if (built & 2u) for (u32 k = lane; k < 256; k += 32) to[256 + k] = from[256 + k];
+    if (built & 4u) for (u32 k = lane; k < 128; k += 32) to[512 + k] = from[512 + k];
   }
 }
 
@@ -207,15 +240,11 @@ __global__ void __launch_bounds__(32) k_huf_decode(const u8* __restrict__ src, c
 // warp-uniform number of steps (the minimum left over the active lanes), so there is no per-step
 // completion test. A lane that finishes its frame pulls the next one from the work list and the
 // warp copies that frame's tables in cooperatively.
-constexpr u32 kSeqSlotEntries = 1280;  // ll 512 + ml 512 + of 256
-constexpr u32 kSeqSlotsMax = 88;       // frames resident per CTA: 88 x 2560 B + LUTs = 220.5 KiB of the SM's 227 KiB
-constexpr u32 kSeqThreads = 96;        // three warps; lanes >= kSeqSlots idle
-constexpr u32 seq_smem_bytes(u32 slots) { return slots * kSeqSlotEntries * sizeof(CSym) + 128 * sizeof(u32) + kRingWords * kSeqThreads * sizeof(u32); }
-static_assert(seq_smem_bytes(kSeqSlotsMax) <= 227 * 1024, "k_seq_decode shared memory");
+constexpr u32 kSeqSlots = 88;          // frames resident per CTA: 88 x 2560 B + LUTs = 220.5 KiB of the SM's 227 KiB
+constexpr u32 kSeqThreads = 96;        // three warps; lanes 88..95 idle
+constexpr u32 kSeqWarpSmem = kSeqSlots * kSeqSlotEntries * sizeof(CSym) + 128 * sizeof(u32) + kRingWords * kSeqThreads * sizeof(u32);
+static_assert(kSeqWarpSmem <= 227 * 1024, "k_seq_decode shared memory");
 
-// kSeqSlots: 88 fills the SM; 78 / 72 / 64 leave room for 2 / 3 / 5 Huffman warps (k_huf_decode, 10 KiB + 1 KiB
-// reserved each) to be resident beside it when that stage runs on the side stream.
-template <u32 kSeqSlots>
 __global__ void __launch_bounds__(kSeqThreads) k_seq_decode(const u8* __restrict__ src, const FrameDesc* __restrict__ descs,
                                                    FrameCtx* __restrict__ ctxs, const FrameTables* __restrict__ tabs,
                                                    u64* __restrict__ seqs, u32 seqStride, RoundWork* __restrict__ work,
@@ -430,13 +459,11 @@ constexpr u32 kTileBytes = 4096;
 constexpr u32 kTileStride = kTileBytes + 32;
 constexpr u32 kShortMax = 64;  // sequences with ll and ml below this go through the tile
 
-enum ExecFlags : u32 { XF_PF_LIT = 1, XF_PF_MATCH = 2 };
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-
-template <int MINB>
-__global__ void __launch_bounds__(kExecWarps * 32, MINB) k_seq_execute(const u8* __restrict__ src, u8* dst, const FrameDesc* __restrict__ descs,
+// Tried and measured slower (profiles/r01f): prefetching the next group's literals / match sources into L1
+// (2.58 -> 2.69 .. 2.74 ms) and 5 CTAs per SM at 48 registers (3.07 ms).
+__global__ void __launch_bounds__(kExecWarps * 32, 4) k_seq_execute(const u8* __restrict__ src, u8* dst, const FrameDesc* __restrict__ descs,
                                                      const FrameCtx* __restrict__ ctxs, const u8* __restrict__ lit, u32 litStride,
-                                                     const u64* __restrict__ seqs, u32 seqStride, u32 nFrames, u32 xflags) {
+                                                     const u64* __restrict__ seqs, u32 seqStride, u32 nFrames) {
   __shared__ __align__(16) u8 tiles[kExecWarps][kTileStride];
   u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   u32 lane = threadIdx.x & 31;
@@ -479,23 +506,6 @@ __global__ void __launch_bounds__(kExecWarps * 32, MINB) k_seq_execute(const u8*
     if (lane == 0) p = carry;
     const u32 S0 = rec_out_end(carry);  // block-relative start of this group's output
     carry = shfl64(s, 31);
-    if (xflags && base + 32 < nbSeq) {
-      // the next group's inputs are requested into L1 a whole iteration ahead: its literals (contiguous in the
-      // literal buffer, from this group's literal end) and every lane's match source (earlier output of this
-      // frame, normally an L2 hit); a line that this group still writes is simply updated by the stores
-      if ((xflags & XF_PF_LIT) && !rle && lane < 2) {
-        const u32 at = rec_lit_end(carry) + 128u * lane;
-        if (at < c.litSize) prefetch_l1(litp + at);
-      }
-      if (xflags & XF_PF_MATCH) {
-        u64 pn = shfl64_up1(sNext);
-        if (lane == 0) pn = carry;
-        const u32 lln = rec_lit_end(sNext) - rec_lit_end(pn);
-        const u32 mposn = rec_out_end(pn) + lln;
-        const u32 offn = rec_off(sNext);
-        if (rec_out_end(sNext) > mposn && offn <= blkDst + mposn) prefetch_l1(blk + mposn - offn);
-      }
-    }
     const u32 S = rec_out_end(carry) - S0;
     const u32 pl = rec_lit_end(p), po = rec_out_end(p);
     const u32 ll = rec_lit_end(s) - pl;
@@ -743,20 +753,11 @@ static int sm_count() {
   return n;
 }
 
-static u32 env_u32(const char* name, u32 dflt) {
-  const char* s = getenv(name);
-  return s ? (u32)strtoul(s, nullptr, 10) : dflt;
-}
-static u32 exec_flags() { static u32 v = env_u32("ZRA_B200_EXEC_FLAGS", 0); return v; }
-static u32 exec_occupancy() { static u32 v = env_u32("ZRA_B200_EXEC_OCC", 4); return v; }
-
 static void configure_kernels() {
   // per device; cheap enough to repeat on every launch sequence
-  cudaFuncSetAttribute(k_seq_decode<88>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem_bytes(88));
-  cudaFuncSetAttribute(k_seq_decode<78>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem_bytes(78));
-  cudaFuncSetAttribute(k_seq_decode<72>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem_bytes(72));
-  cudaFuncSetAttribute(k_seq_decode<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seq_smem_bytes(64));
+  cudaFuncSetAttribute(k_seq_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSeqWarpSmem);
   cudaFuncSetAttribute(k_huf_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHufWarpSmem);
+  cudaFuncSetAttribute(k_block_setup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSetupSmem);
 }
 
 size_t decode_scratch_bytes(u32 nFrames, u32 maxDstCap, DecodeLayout* lay) {
@@ -798,7 +799,7 @@ void launch_summary_reset(void* scratch, const DecodeLayout& lay, cudaStream_t s
 }
 
 void launch_decode_rounds(const void* src, void* dst, u32 nFrames, u32 rounds, bool first, void* scratch, const DecodeLayout& lay,
-                          cudaStream_t st, KernelTimer* timer, const SideLane* side) {
+                          cudaStream_t st, KernelTimer* timer) {
   if (!nFrames) return;
   configure_kernels();
   u8* s = static_cast<u8*>(scratch);
@@ -814,43 +815,22 @@ void launch_decode_rounds(const void* src, void* dst, u32 nFrames, u32 rounds, b
   const u32 sms = (u32)sm_count();
   // persistent grids: as many warps as fit the SMs' shared memory, never more than there is work
   const u32 hufWarps = sms * 20 < div_up(nFrames, 8) ? sms * 20 : div_up(nFrames, 8);
-  static const u32 forkHuf = env_u32("ZRA_B200_FORK_HUF", 0);
-  if (timer || !forkHuf) side = nullptr;  // per-kernel timing wants one stream
-  static const u32 slotsEnv = env_u32("ZRA_B200_SEQ_SLOTS", 0);
-  const u32 slots = slotsEnv == 64 || slotsEnv == 72 || slotsEnv == 78 || slotsEnv == 88 ? slotsEnv : (side ? 72u : 88u);
-  const u32 seqCtas = sms < div_up(nFrames, slots) ? sms : div_up(nFrames, slots);
+  // Tried and measured slower (profiles/r01i): running the Huffman stage on a side stream beside the sequence stage
+  // (with 78 / 72 / 64 slots to leave it shared memory): the Huffman warps take issue slots and shared-memory
+  // bandwidth from the latency-critical sequence warps (6.43 -> 6.9 .. 7.8 ms per step).
+  const u32 seqCtas = sms < div_up(nFrames, kSeqSlots) ? sms : div_up(nFrames, kSeqSlots);
   for (u32 r = 0; r < rounds; r++) {
     cudaMemsetAsync(work, 0, sizeof(RoundWork), st);
     ZRA_MARK(K_START);
-    k_block_setup<<<div_up(nFrames, 64), 64, 0, st>>>(in, descs, ctxs, tabs, nFrames, (first && r == 0) ? 1u : 0u, work, hufList,
-                                                      seqList);
+    k_block_setup<<<div_up(nFrames, 32), 32, kSetupSmem, st>>>(in, descs, ctxs, tabs, nFrames, (first && r == 0) ? 1u : 0u, work, hufList,
+                                                               seqList);
     ZRA_MARK(K_BLOCK_SETUP);
-    // the sequence stage goes first so that its whole-SM CTAs are placed before the Huffman warps fill the rest
-    cudaStream_t hs = st;
-    if (side) {
-      cudaEventRecord(side->setupDone, st);
-      hs = side->st;
-    } else {
-      k_huf_decode<<<hufWarps, 32, kHufWarpSmem, st>>>(in, descs, ctxs, tabs, lit, lay.litStride, work, hufList);
-      ZRA_MARK(K_HUF_DECODE);
-    }
-    if (slots == 88) k_seq_decode<88><<<seqCtas, kSeqThreads, seq_smem_bytes(88), st>>>(in, descs, ctxs, tabs, seqs, lay.seqStride, work, seqList);
-    else if (slots == 78) k_seq_decode<78><<<seqCtas, kSeqThreads, seq_smem_bytes(78), st>>>(in, descs, ctxs, tabs, seqs, lay.seqStride, work, seqList);
-    else if (slots == 72) k_seq_decode<72><<<seqCtas, kSeqThreads, seq_smem_bytes(72), st>>>(in, descs, ctxs, tabs, seqs, lay.seqStride, work, seqList);
-    else k_seq_decode<64><<<seqCtas, kSeqThreads, seq_smem_bytes(64), st>>>(in, descs, ctxs, tabs, seqs, lay.seqStride, work, seqList);
+    k_huf_decode<<<hufWarps, 32, kHufWarpSmem, st>>>(in, descs, ctxs, tabs, lit, lay.litStride, work, hufList);
+    ZRA_MARK(K_HUF_DECODE);
+    k_seq_decode<<<seqCtas, kSeqThreads, kSeqWarpSmem, st>>>(in, descs, ctxs, tabs, seqs, lay.seqStride, work, seqList);
     ZRA_MARK(K_SEQ_DECODE);
-    if (side) {
-      cudaStreamWaitEvent(hs, side->setupDone, 0);
-      k_huf_decode<<<hufWarps, 32, kHufWarpSmem, hs>>>(in, descs, ctxs, tabs, lit, lay.litStride, work, hufList);
-      cudaEventRecord(side->hufDone, hs);
-      cudaStreamWaitEvent(st, side->hufDone, 0);
-    }
-    if (exec_occupancy() >= 5)
-      k_seq_execute<5><<<div_up((u64)nFrames * 32, kExecWarps * 32), kExecWarps * 32, 0, st>>>(in, static_cast<u8*>(dst), descs, ctxs, lit, lay.litStride,
-                                                                      seqs, lay.seqStride, nFrames, exec_flags());
-    else
-      k_seq_execute<4><<<div_up((u64)nFrames * 32, kExecWarps * 32), kExecWarps * 32, 0, st>>>(in, static_cast<u8*>(dst), descs, ctxs, lit, lay.litStride,
-                                                                      seqs, lay.seqStride, nFrames, exec_flags());
+    k_seq_execute<<<div_up((u64)nFrames * 32, kExecWarps * 32), kExecWarps * 32, 0, st>>>(in, static_cast<u8*>(dst), descs, ctxs, lit, lay.litStride, seqs,
+                                                                 lay.seqStride, nFrames);
     ZRA_MARK(K_SEQ_EXECUTE);
   }
 }

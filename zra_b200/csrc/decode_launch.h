@@ -50,16 +50,9 @@ void launch_build_descs(const void* archive, uint64_t tableOff, uint64_t headerS
                         uint64_t uncompressedSize, uint32_t frameSize, uint32_t firstFrame, uint32_t nFrames, uint64_t dstBase,
                         void* scratch, const DecodeLayout& lay, cudaStream_t st, KernelTimer* timer = nullptr);
 
-// A second stream and two events of the caller's: with them the Huffman literal stage of a round runs BESIDE the
-// sequence stage (both only depend on the setup kernel) instead of before it.
-struct SideLane {
-  cudaStream_t st;
-  cudaEvent_t setupDone, hufDone;
-};
-
 // Runs `rounds` rounds (one block of every frame per round). `first` resets the frame contexts.
 void launch_decode_rounds(const void* src, void* dst, uint32_t nFrames, uint32_t rounds, bool first, void* scratch,
-                          const DecodeLayout& lay, cudaStream_t st, KernelTimer* timer = nullptr, const SideLane* side = nullptr);
+                          const DecodeLayout& lay, cudaStream_t st, KernelTimer* timer = nullptr);
 
 // Checksums + final checks + summary. May be called again after extra rounds.
 void launch_frame_finish(const void* src, const void* dst, uint32_t nFrames, void* scratch, const DecodeLayout& lay,

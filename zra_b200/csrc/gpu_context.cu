@@ -33,9 +33,6 @@ GpuContext::GpuContext(int device) {
     for (int i = 0; i < kPoolStreams; i++) {
       int prio = flat ? least : std::min(least, greatest + i);
       if (check(cudaStreamCreateWithPriority(&pool_[i], cudaStreamNonBlocking, prio), "cudaStreamCreate")) return;
-      if (check(cudaStreamCreateWithPriority(&side_[i].st, cudaStreamNonBlocking, prio), "cudaStreamCreate")) return;
-      if (check(cudaEventCreateWithFlags(&side_[i].setupDone, cudaEventDisableTiming), "cudaEventCreate")) return;
-      if (check(cudaEventCreateWithFlags(&side_[i].hufDone, cudaEventDisableTiming), "cudaEventCreate")) return;
     }
   }
   if (check(cudaEventCreateWithFlags(&forkEvent_, cudaEventDisableTiming), "cudaEventCreate")) return;
@@ -51,11 +48,6 @@ GpuContext::~GpuContext() {
     if (b->p) cudaFree(b->p);
   for (auto& s : pool_)
     if (s) cudaStreamDestroy(s);
-  for (auto& l : side_) {
-    if (l.st) cudaStreamDestroy(l.st);
-    if (l.setupDone) cudaEventDestroy(l.setupDone);
-    if (l.hufDone) cudaEventDestroy(l.hufDone);
-  }
   if (forkEvent_) cudaEventDestroy(forkEvent_);
   if (summaryHost_) cudaFreeHost(summaryHost_);
   if (stream_) cudaStreamDestroy(stream_);
@@ -109,8 +101,9 @@ static uint32_t chunk_target() {
   return v;
 }
 
-// Host-pointer calls (uploads and downloads inside the chunk pipeline) are PCIe-bound: the time before the
-// first download can start is one chunk's upload + decode, so they are cut finer than device-resident calls.
+// Host-pointer calls (uploads and downloads inside the chunk pipeline) are PCIe-bound. Finer or geometrically
+// growing chunks were measured SLOWER (profiles/r01e, r01h): every chunk's kernels take about the same time whatever
+// its size (serial per-frame chains), and more chunks in flight only delay each other's tails.
 static uint32_t io_chunk_target() {
   static uint32_t v = [] {
     const char* s = getenv("ZRA_B200_IO_CHUNKS");
@@ -127,7 +120,6 @@ namespace {
     DecodeLayout lay;
     uint8_t* scratch;
     cudaStream_t st;
-    const SideLane* side;
     uint32_t* summary;  // pinned host words
   };
 }  // namespace
@@ -179,15 +171,6 @@ DecodeResult GpuContext::decode(const void* dSrc, size_t srcSize, const HostFram
         if (*q == ',') q++; else break;
       }
       if (c0 < gN) add_chunk(c0, gN - c0);
-    } else if (hostIo && !single && gN >= 2048 && getenv("ZRA_B200_IO_GEOMETRIC")) {
-      // host-pointer calls are PCIe-bound and every chunk's kernels take about the same time whatever its size
-      // (serial per-frame chains), so the first download can only start one upload + one kernel latency into the
-      // call: a small first chunk starts it early, and the sizes grow geometrically so that each later chunk
-      // is decoded by the time the downloads before it have drained (1/32, 1/16, 1/8, 1/4, 1/4, rest).
-      const uint64_t cut[5] = {gN / 32, gN / 16, gN / 8, gN / 4, gN / 4};
-      uint64_t c0 = 0;
-      for (uint64_t n : cut) { add_chunk(c0, n); c0 += n; }
-      add_chunk(c0, gN - c0);
     } else {
       for (uint64_t c0 = 0; c0 < gN; c0 += per) add_chunk(c0, std::min<uint64_t>(per, gN - c0));
     }
@@ -199,8 +182,6 @@ DecodeResult GpuContext::decode(const void* dSrc, size_t srcSize, const HostFram
       chunks[i].scratch = base + off;
       off += decode_scratch_bytes(chunks[i].n, maxDstCap, &tmp);
       chunks[i].st = single ? st : pool_[i % kPoolStreams];
-      // the side lane's events are per pool stream: only the first kPoolStreams chunks (one per stream) fork
-      chunks[i].side = (single || i >= (size_t)kPoolStreams) ? nullptr : &side_[i];
       chunks[i].summary = summaryHost_ + 4 * i;
     }
     // ---- fork: the pool streams start after whatever the caller queued on `st`
@@ -248,7 +229,7 @@ DecodeResult GpuContext::decode(const void* dSrc, size_t srcSize, const HostFram
                            (uint32_t)(firstFrame + c.f0), c.n, firstFrame * info->frameSize, c.scratch, c.lay, c.st, tm);
         launches_ += 1;
       }
-      launch_decode_rounds(dSrc, dDst, c.n, baseRounds, true, c.scratch, c.lay, c.st, tm, c.side);
+      launch_decode_rounds(dSrc, dDst, c.n, baseRounds, true, c.scratch, c.lay, c.st, tm);
       launches_ += 4ull * baseRounds;
       if (!enqueue_tail(c)) return fail_cuda();
     }

@@ -119,7 +119,6 @@ class GpuContext {
   bool profiling_{false};
   static constexpr int kPoolStreams = 16;
   cudaStream_t pool_[kPoolStreams] = {};
-  SideLane side_[kPoolStreams] = {};  // per pool stream: the stream + events of the forked Huffman stage
   cudaEvent_t forkEvent_{nullptr};
   uint32_t* summaryHost_{nullptr};  // pinned, 4 words per chunk
   uint32_t* raHost_{nullptr};       // pinned, {unique frames, first bad request}
