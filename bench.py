@@ -44,6 +44,8 @@ def parse_args():
     ap.add_argument("--no-ra", action="store_true", help="skip the batched random-access leg")
     ap.add_argument("--ra-size-mib", type=int, default=1024, help="original bytes of the random-access archive (16 KiB frames)")
     ap.add_argument("--no-compress", action="store_true", help="skip the CompressBuffer leg")
+    ap.add_argument("--no-streaming", action="store_true", help="skip the FullDecompressor streaming leg")
+    ap.add_argument("--stream-size-mib", type=int, default=1024, help="original bytes of the streaming archive (256 KiB frames)")
     ap.add_argument("--compress-size-mib", type=int, default=1024, help="bytes of mixed data per GPU for the CompressBuffer leg")
     return ap.parse_args()
 
@@ -385,6 +387,96 @@ def run_compress(args, torch, dist, ctx, rank, world, peak):
     return out
 
 
+# ---------------------------------------------------------------- FullDecompressor streaming (BASELINE configs[4] shape)
+def run_streaming(args, torch, dist, rank, world):
+    """zra::FullDecompressor over the C ABI (ZraCreateFullDecompressor / ZraDecompressWithFullDecompressor): an archive of
+    256 KiB frames is streamed through the reference's read-callback model (the callback memcpy's from a host copy of
+    the archive, once per Decompress call, synchronously on the caller's thread) into a pinned 256 MiB output buffer,
+    call after call until it returns 0. Host pointers in, host pointers out: uploads and downloads are inside the timing."""
+    import ctypes as C
+
+    import zra_b200
+    from zra_b200 import binding
+
+    fs = 262144
+    size = args.stream_size_mib << 20
+    data, archive = build_archive(size, fs, 3, seed=207 + rank)
+    base = archive.ctypes.data
+    calls = [0]
+
+    def cb(offset, nbytes, buf):
+        calls[0] += 1
+        C.memmove(buf, base + offset, nbytes)
+
+    reader = binding.READ_FN(cb)
+    L = zra_b200.lib()
+    out = torch.empty(min(size, 256 << 20), dtype=torch.uint8).pin_memory()
+    result = np.empty(size, np.uint8)
+
+    def one_pass(keep):
+        h = C.c_void_p()
+        st = L.ZraCreateFullDecompressor(C.byref(h), reader, 0)
+        assert st.zra == 0, (st.zra, st.zstd)
+        pos = 0
+        n = C.c_size_t(0)
+        while True:
+            st = L.ZraDecompressWithFullDecompressor(h, C.c_void_p(out.data_ptr()), out.numel(), C.byref(n))
+            assert st.zra == 0, (st.zra, st.zstd)
+            if not n.value:
+                break
+            if keep:
+                result[pos: pos + n.value] = out.numpy()[: n.value]
+            pos += n.value
+        L.ZraDeleteFullDecompressor(h)
+        return pos
+
+    assert one_pass(True) == size and np.array_equal(result, data), "streamed output differs from the original"
+    steps = max(2, min(args.steps, 5))
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_pass(False)
+    dt = (time.perf_counter() - t0) / steps
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    res = {"metric": "FullDecompressor streaming GB/s", "value": round(world * size / dt / 1e9, 3), "unit": "GB/s",
+           "ms_per_pass": round(dt * 1e3, 3),
+           "config": {"workload": f"zra::FullDecompressor, {args.stream_size_mib} MiB Zipf-text archive per GPU, 262144 B frames, level 3, "
+                                  f"read callback = memcpy from a host copy, {out.numel() >> 20} MiB pinned output buffer per call "
+                                  "(configs[4] shape; frame ranges = archives per rank at N > 1)",
+                      "read_callbacks_per_pass": calls[0] // (steps + 1)},
+           "h2d_bytes_per_pass": int(archive.size), "d2h_bytes_per_pass": int(size)}
+    if rank == 0 and not args.no_cpu_baseline:
+        try:
+            import refzra
+
+            R = refzra.ref()
+            R.ZraCreateFullDecompressor.argtypes = [C.POINTER(C.c_void_p), binding.READ_FN, C.c_size_t]
+            R.ZraCreateFullDecompressor.restype = R.St
+            R.ZraDecompressWithFullDecompressor.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+            R.ZraDecompressWithFullDecompressor.restype = R.St
+            R.ZraDeleteFullDecompressor.argtypes = [C.c_void_p]
+            h = C.c_void_p()
+            assert R.ZraCreateFullDecompressor(C.byref(h), reader, 0).zra == 0
+            n = C.c_size_t(0)
+            host = np.empty(out.numel(), np.uint8)
+            host[:] = 0
+            t0 = time.perf_counter()
+            assert R.ZraDecompressWithFullDecompressor(h, host.ctypes.data, host.size, C.byref(n)).zra == 0
+            dtc = time.perf_counter() - t0
+            R.ZraDeleteFullDecompressor(h)
+            assert np.array_equal(host[: n.value], data[: n.value])
+            res["cpu_baseline"] = {"value": round(n.value / dtc / 1e9, 4), "unit": "GB/s", "cores": 1, "kind": "reference",
+                                   "sample": f"the first Decompress call ({n.value >> 20} MiB) of the reference's zra::FullDecompressor "
+                                             "(single-threaded by construction)"}
+        except Exception as e:  # noqa: BLE001
+            res["cpu_baseline"] = {"value": None, "sample": f"failed: {e}"}
+    return res
+
+
 def zra_b200_cap(size, frame_size):
     import zra_b200
     return int(zra_b200.GetOutputBufferSize(size, frame_size))
@@ -568,6 +660,13 @@ def run_gpu(args):
         except Exception as e:  # never take the headline down
             comp = {"metric": "compress GB/s", "value": None, "unit": "GB/s", "error": repr(e)}
 
+    streaming = None
+    if not args.no_streaming:
+        try:
+            streaming = run_streaming(args, torch, dist, rank, world)
+        except Exception as e:  # never take the headline down
+            streaming = {"metric": "FullDecompressor streaming GB/s", "value": None, "unit": "GB/s", "error": repr(e)}
+
     if rank == 0:
         line = {
             "metric": "decompress GB/s", "value": round(value, 3), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
@@ -594,6 +693,8 @@ def run_gpu(args):
             line["random_access"] = ra
         if comp is not None:
             line["compress"] = comp
+        if streaming is not None:
+            line["streaming"] = streaming
         if world == 1 and not args.no_cpu_baseline:
             try:
                 threads = os.cpu_count() or 1

@@ -135,45 +135,48 @@ ZRA_DEV u32 setup_seq_table(CSym* table, u32* logOut, u32 type, u32 kind, const 
 }
 
 // ---------------------------------------------------------------- block_setup (1 thread / frame)
-// Where block_setup builds the three sequence tables: straight into the frame's FrameTables (stage == nullptr), or
-// into a caller-provided staging area (the kernel: shared memory; `built` then tells which tables were rebuilt
-// this round and must be copied out — a "repeat" table keeps the previous block's copy in FrameTables).
-struct SeqTableStage {
-  CSym *ll, *ml, *of;
-  u32 built;  // bit 0: ll, bit 1: ml, bit 2: of
+// block_setup in three steps, so that a kernel can build ONE sequence table at a time in a small shared-memory
+// staging area and copy it out (warp-cooperatively) before the next: head (headers, literals section, sequence
+// section header), table x 3 in stream order (LL, OF, ML), tail. `SetupCursor` carries the parse position between
+// the steps; live == false means the block needs no (more) table work — finished, failed, raw, RLE or sequence-free.
+struct SetupCursor {
+  u32 ip, iend;   // offsets within the frame of the next unread byte / the end of the block content
+  u32 modes, nbSeq;
+  bool live;
 };
 
-ZRA_DEV void block_setup(const u8* srcBase, const FrameDesc& d, FrameCtx& c, FrameTables& t, bool firstRound,
-                         SeqTableStage* stage = nullptr) {
+ZRA_DEV SetupCursor block_setup_head(const u8* srcBase, const FrameDesc& d, FrameCtx& c, FrameTables& t, bool firstRound) {
+  SetupCursor cur;
+  cur.ip = cur.iend = cur.modes = cur.nbSeq = 0;
+  cur.live = false;
   const u8* f = srcBase + d.srcOff;
-  if (stage) stage->built = 0;
-  if (firstRound) { if (!parse_frame_header(f, d, c)) return; }
+  if (firstRound) { if (!parse_frame_header(f, d, c)) return cur; }
   c.blkType = BT_NONE;
-  if (c.status || (c.flags & FF_DONE)) return;
+  if (c.status || (c.flags & FF_DONE)) return cur;
   u32 tail = (c.flags & FF_CHECKSUM) ? 4u : 0u;
   (void)tail;
-  if (c.srcPos + 3 > d.srcLen) { frame_fail(c, ZE_SRC_WRONG); return; }
+  if (c.srcPos + 3 > d.srcLen) { frame_fail(c, ZE_SRC_WRONG); return cur; }
   u32 bh = ld24(f + c.srcPos);
   u32 last = bh & 1, type = (bh >> 1) & 3, bsz = bh >> 3;
-  if (type == 3) { frame_fail(c, ZE_CORRUPTION); return; }
+  if (type == 3) { frame_fail(c, ZE_CORRUPTION); return cur; }
   u32 csz = (type == BT_RLE) ? 1 : bsz;
   u32 content = c.srcPos + 3;
-  if (content + csz > d.srcLen) { frame_fail(c, ZE_SRC_WRONG); return; }
+  if (content + csz > d.srcLen) { frame_fail(c, ZE_SRC_WRONG); return cur; }
   c.blkSrc = content;
   c.blkSize = bsz;
   c.blkDst = c.dstPos;
   c.srcPos = content + csz;
   if (last) c.flags |= FF_DONE;
   if (type != BT_COMPRESSED) {
-    if (bsz > d.dstCap - c.dstPos) { frame_fail(c, ZE_DST_TOO_SMALL); return; }
+    if (bsz > d.dstCap - c.dstPos) { frame_fail(c, ZE_DST_TOO_SMALL); return cur; }
     c.blkType = type;
     c.blkOut = bsz;
     c.dstPos += bsz;
-    return;
+    return cur;
   }
   // ---- compressed block
-  if (csz >= kBlockSizeMax) { frame_fail(c, ZE_SRC_WRONG); return; }
-  if (csz < 3) { frame_fail(c, ZE_CORRUPTION); return; }
+  if (csz >= kBlockSizeMax) { frame_fail(c, ZE_SRC_WRONG); return cur; }
+  if (csz < 3) { frame_fail(c, ZE_CORRUPTION); return cur; }
   const u8* b = f + content;
   u32 used;
   c.nStreams = 0;
@@ -182,19 +185,19 @@ ZRA_DEV void block_setup(const u8* srcBase, const FrameDesc& d, FrameCtx& c, Fra
     if (ltype >= 2) {
       u32 lh, cs, litSize;
       bool single = false;
-      if (ltype == 3 && !(c.flags & FF_HUF_VALID)) { frame_fail(c, ZE_DICT_CORRUPTED); return; }
-      if (csz < 5) { frame_fail(c, ZE_CORRUPTION); return; }
+      if (ltype == 3 && !(c.flags & FF_HUF_VALID)) { frame_fail(c, ZE_DICT_CORRUPTED); return cur; }
+      if (csz < 5) { frame_fail(c, ZE_CORRUPTION); return cur; }
       u32 w = ld32(b);
       if (fmt <= 1) { single = !fmt; lh = 3; litSize = (w >> 4) & 0x3FF; cs = (w >> 14) & 0x3FF; }
       else if (fmt == 2) { lh = 4; litSize = (w >> 4) & 0x3FFF; cs = w >> 18; }
       else { lh = 5; litSize = (w >> 4) & 0x3FFFF; cs = (w >> 22) + ((u32)b[4] << 10); }
-      if (litSize > kBlockSizeMax || cs + lh > csz) { frame_fail(c, ZE_CORRUPTION); return; }
+      if (litSize > kBlockSizeMax || cs + lh > csz) { frame_fail(c, ZE_CORRUPTION); return cur; }
       u32 hoff = content + lh, hlen = cs;
       if (ltype == 2) {
         u8 weights[256];
         u32 count, log;
         u32 h = huf_read_weights(srcBase, d.srcOff + hoff, hlen, weights, &count, &log);
-        if (!h || !huf_check_weights(weights, count)) { frame_fail(c, ZE_CORRUPTION); return; }
+        if (!h || !huf_check_weights(weights, count)) { frame_fail(c, ZE_CORRUPTION); return cur; }
         // the decode table itself is built by the Huffman stage, straight into shared memory
         for (u32 i = 0; i < count; i++) t.hufWeights[i] = weights[i];
         c.hufCount = count;
@@ -206,12 +209,12 @@ ZRA_DEV void block_setup(const u8* srcBase, const FrameDesc& d, FrameCtx& c, Fra
         c.nStreams = 1;
         c.strOff[0] = hoff; c.strLen[0] = hlen;
       } else {
-        if (hlen < 10) { frame_fail(c, ZE_CORRUPTION); return; }
+        if (hlen < 10) { frame_fail(c, ZE_CORRUPTION); return cur; }
         const u8* j = f + hoff;
         u32 l1 = ld16(j), l2 = ld16(j + 2), l3 = ld16(j + 4);
-        if (l1 + l2 + l3 + 6 > hlen) { frame_fail(c, ZE_CORRUPTION); return; }
+        if (l1 + l2 + l3 + 6 > hlen) { frame_fail(c, ZE_CORRUPTION); return cur; }
         u32 seg = (litSize + 3) / 4;
-        if (seg * 3 > litSize) { frame_fail(c, ZE_CORRUPTION); return; }
+        if (seg * 3 > litSize) { frame_fail(c, ZE_CORRUPTION); return cur; }
         c.nStreams = 4;
         c.strOff[0] = hoff + 6; c.strLen[0] = l1;
         c.strOff[1] = c.strOff[0] + l1; c.strLen[1] = l2;
@@ -226,11 +229,11 @@ ZRA_DEV void block_setup(const u8* srcBase, const FrameDesc& d, FrameCtx& c, Fra
       else if (fmt == 1) { lh = 2; litSize = ld16(b) >> 4; }
       else { lh = 3; litSize = ld24(b) >> 4; }
       if (ltype == 0) {
-        if (lh + litSize > csz) { frame_fail(c, ZE_CORRUPTION); return; }
+        if (lh + litSize > csz) { frame_fail(c, ZE_CORRUPTION); return cur; }
         c.litMode = LIT_RAW; c.litSrc = content + lh; c.litSize = litSize;
         used = lh + litSize;
       } else {
-        if (lh + 1 > csz || litSize > kBlockSizeMax) { frame_fail(c, ZE_CORRUPTION); return; }
+        if (lh + 1 > csz || litSize > kBlockSizeMax) { frame_fail(c, ZE_CORRUPTION); return cur; }
         c.litMode = LIT_RLE; c.litSrc = b[lh]; c.litSize = litSize;
         used = lh + 1;
       }
@@ -239,46 +242,72 @@ ZRA_DEV void block_setup(const u8* srcBase, const FrameDesc& d, FrameCtx& c, Fra
   // ---- sequences section header
   const u8* ip = b + used;
   const u8* iend = b + csz;
-  if (ip >= iend) { frame_fail(c, ZE_SRC_WRONG); return; }
+  if (ip >= iend) { frame_fail(c, ZE_SRC_WRONG); return cur; }
   u32 nbSeq = *ip++;
   if (!nbSeq) {
-    if (ip != iend) { frame_fail(c, ZE_SRC_WRONG); return; }
+    if (ip != iend) { frame_fail(c, ZE_SRC_WRONG); return cur; }
   } else {
     if (nbSeq > 0x7F) {
       if (nbSeq == 0xFF) {
-        if (ip + 2 > iend) { frame_fail(c, ZE_SRC_WRONG); return; }
+        if (ip + 2 > iend) { frame_fail(c, ZE_SRC_WRONG); return cur; }
         nbSeq = ld16(ip) + kLongNbSeq; ip += 2;
       } else {
-        if (ip >= iend) { frame_fail(c, ZE_SRC_WRONG); return; }
+        if (ip >= iend) { frame_fail(c, ZE_SRC_WRONG); return cur; }
         nbSeq = ((nbSeq - 0x80) << 8) + *ip++;
       }
     }
-    if (ip + 1 > iend) { frame_fail(c, ZE_SRC_WRONG); return; }
-    u32 modes = *ip++;
-    bool rep = (c.flags & FF_FSE_VALID) != 0;
-    u32 h = setup_seq_table(stage ? stage->ll : t.ll, &c.llLog, modes >> 6, SEQ_LL, ip, (u32)(iend - ip), rep);
-    if (h == 0xFFFFFFFFu) { frame_fail(c, ZE_CORRUPTION); return; }
-    ip += h;
-    h = setup_seq_table(stage ? stage->of : t.of, &c.ofLog, (modes >> 4) & 3, SEQ_OF, ip, (u32)(iend - ip), rep);
-    if (h == 0xFFFFFFFFu) { frame_fail(c, ZE_CORRUPTION); return; }
-    ip += h;
-    h = setup_seq_table(stage ? stage->ml : t.ml, &c.mlLog, (modes >> 2) & 3, SEQ_ML, ip, (u32)(iend - ip), rep);
-    if (h == 0xFFFFFFFFu) { frame_fail(c, ZE_CORRUPTION); return; }
-    ip += h;
-    if (stage) stage->built = ((modes >> 6) != 3 ? 1u : 0u) | (((modes >> 2) & 3) != 3 ? 2u : 0u) | (((modes >> 4) & 3) != 3 ? 4u : 0u);
-    c.flags |= FF_FSE_VALID;
-    if (ip >= iend) { frame_fail(c, ZE_CORRUPTION); return; }  // the bitstream needs at least its end mark
+    if (ip + 1 > iend) { frame_fail(c, ZE_SRC_WRONG); return cur; }
+    cur.modes = *ip++;
+    cur.live = true;
   }
-  c.nbSeq = nbSeq;
-  c.seqOff = (u32)(ip - f);
-  c.seqLen = (u32)(iend - ip);
+  cur.nbSeq = nbSeq;
+  cur.ip = (u32)(ip - f);
+  cur.iend = (u32)(iend - f);
+  return cur;
+}
+
+// One table (kind in stream order: SEQ_LL, SEQ_OF, SEQ_ML) into `dst` (the frame's FrameTables array, or a staging
+// copy of it). Returns true when `dst` was (re)built; a "repeat" table keeps the previous block's copy.
+ZRA_DEV bool block_setup_table(const u8* srcBase, const FrameDesc& d, FrameCtx& c, SetupCursor& cur, u32 kind, CSym* dst) {
+  if (!cur.live) return false;
+  const u8* f = srcBase + d.srcOff;
+  const u32 type = kind == SEQ_LL ? cur.modes >> 6 : (kind == SEQ_OF ? (cur.modes >> 4) & 3 : (cur.modes >> 2) & 3);
+  u32* logOut = kind == SEQ_LL ? &c.llLog : (kind == SEQ_OF ? &c.ofLog : &c.mlLog);
+  const bool rep = (c.flags & FF_FSE_VALID) != 0;
+  const u32 h = setup_seq_table(dst, logOut, type, kind, f + cur.ip, cur.iend - cur.ip, rep);
+  if (h == 0xFFFFFFFFu) { frame_fail(c, ZE_CORRUPTION); cur.live = false; return false; }
+  cur.ip += h;
+  return type != 3;
+}
+
+ZRA_DEV void block_setup_tail(const FrameDesc& d, FrameCtx& c, SetupCursor& cur) {
+  if (c.status || c.blkType == BT_RAW || c.blkType == BT_RLE) return;
+  if (cur.nbSeq) {
+    if (!cur.live) return;  // failed in a table
+    c.flags |= FF_FSE_VALID;
+    if (cur.ip >= cur.iend) { frame_fail(c, ZE_CORRUPTION); return; }  // the bitstream needs at least its end mark
+  } else if (cur.iend == 0) {
+    return;  // the head stopped before the sequence section (frame done earlier, nothing to do)
+  }
+  c.nbSeq = cur.nbSeq;
+  c.seqOff = cur.ip;
+  c.seqLen = cur.iend - cur.ip;
   c.blkType = BT_COMPRESSED;
   c.blkOut = 0;
-  if (!nbSeq) {  // literals only: nothing for the sequence stage to do
+  if (!cur.nbSeq) {  // literals only: nothing for the sequence stage to do
     if (c.litSize > d.dstCap - c.blkDst) { frame_fail(c, ZE_DST_TOO_SMALL); return; }
     c.blkOut = c.litSize;
     c.dstPos = c.blkDst + c.litSize;
   }
+}
+
+// Thread-serial whole (host logic tests; frames handled outside the staging kernel).
+ZRA_DEV void block_setup(const u8* srcBase, const FrameDesc& d, FrameCtx& c, FrameTables& t, bool firstRound) {
+  SetupCursor cur = block_setup_head(srcBase, d, c, t, firstRound);
+  block_setup_table(srcBase, d, c, cur, SEQ_LL, t.ll);
+  block_setup_table(srcBase, d, c, cur, SEQ_OF, t.of);
+  block_setup_table(srcBase, d, c, cur, SEQ_ML, t.ml);
+  block_setup_tail(d, c, cur);
 }
 
 // ---------------------------------------------------------------- bit reader

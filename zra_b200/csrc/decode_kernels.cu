@@ -31,6 +31,7 @@ constexpr u32 kNone = 0xFFFFFFFFu;
 struct RoundWork {
   u32 hufCount, seqCount;  // entries appended this round
   u32 hufNext, seqNext;    // consumer cursors
+  u32 seqCountS, seqNextS; // the small-table frames (taken from the back of the sequence list)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -62,50 +63,60 @@ __global__ void k_build_descs(const u8* __restrict__ archive, u64 tableOff, u64 
   descs[i] = d;
 }
 
-// One warp per CTA, one frame per lane. The three sequence tables are BUILT IN SHARED MEMORY (the build is a
+// One warp per CTA, one frame per lane. The sequence tables are BUILT IN SHARED MEMORY (the build is a
 // read-modify-write of every cell: spread the symbols, then number the cells; in HBM scratch each of those 2 x 1280
-// dependent accesses is an L2 round trip) and leave with coalesced word stores by the whole warp. Every lane's
-// staging area is padded by one word so that lanes touching the same cell index fall into different banks.
-constexpr u32 kSeqSlotEntries = 1280;  // ll 512 + ml 512 + of 256 (the sequence tables of one frame)
-constexpr u32 kSetupStageWords = kSeqSlotEntries * sizeof(CSym) / 4 + 1;  // 641
-constexpr u32 kSetupSmem = 32 * kSetupStageWords * 4;                      // 80.1 KiB
+// dependent accesses is an L2 round trip), one table at a time (block_setup_head / _table x 3 / _tail): each lane
+// has a 1 KiB staging area (one word of padding, so that lanes touching the same cell index fall into different
+// banks), and after each table the whole warp copies the rebuilt ones out with coalesced word stores. 32.1 KiB per
+// CTA: seven warps per SM, which is what bounds this kernel on archives of many small frames.
+constexpr u32 kSeqSmallLogMax = 8;     // LL and ML table logs up to this take the small sequence-stage geometry (below)
+constexpr u32 kSetupStageWords = 512 * sizeof(CSym) / 4 + 1;  // 257
+constexpr u32 kSetupSmem = 32 * kSetupStageWords * 4;          // 32.1 KiB
 
 __global__ void __launch_bounds__(32) k_block_setup(const u8* __restrict__ src, const FrameDesc* __restrict__ descs,
                                                     FrameCtx* __restrict__ ctxs, FrameTables* __restrict__ tabs, u32 nFrames,
                                                     u32 firstRound, RoundWork* __restrict__ work, u32* __restrict__ hufList,
-                                                    u32* __restrict__ seqList) {
+                                                    u32* __restrict__ seqList, u32 splitSmall) {
   extern __shared__ __align__(16) u8 smem[];
   u32* stageWords = reinterpret_cast<u32*>(smem);
   const u32 lane = threadIdx.x;
   const u32 i = blockIdx.x * 32 + lane;
-  SeqTableStage stage;
-  stage.ll = reinterpret_cast<CSym*>(stageWords + lane * kSetupStageWords);
-  stage.ml = stage.ll + 512;
-  stage.of = stage.ll + 1024;
-  stage.built = 0;
-  if (i < nFrames) {
-    FrameCtx c = ctxs[i];
-    block_setup(src, descs[i], c, tabs[i], firstRound != 0, &stage);
-    ctxs[i] = c;
-    if (c.blkType == BT_COMPRESSED && !c.status) {
-      if (c.litMode == LIT_HUF && c.litSize) hufList[atomicAdd(&work->hufCount, 1u)] = i;
-      if (c.nbSeq) seqList[atomicAdd(&work->seqCount, 1u)] = i;
-    } else {
-      stage.built = 0;  // nothing will read the tables of a failed / raw / RLE block
-    }
+  const bool have = i < nFrames;
+  CSym* stage = reinterpret_cast<CSym*>(stageWords + lane * kSetupStageWords);
+  FrameCtx c;
+  SetupCursor cur;
+  cur.live = false;
+  if (have) {
+    c = ctxs[i];
+    cur = block_setup_head(src, descs[i], c, tabs[i], firstRound != 0);
   }
-  __syncwarp();
-  // copy-out: lane by lane, the whole warp moves the tables that lane rebuilt (ll 256 words | ml 256 | of 128)
-  u32 any = __ballot_sync(kFull, stage.built != 0);
-  while (any) {
-    const int who = __ffs(any) - 1;
-    any &= any - 1;
-    const u32 built = __shfl_sync(kFull, stage.built, who);
-    const u32* from = stageWords + who * kSetupStageWords;
-    u32* to = reinterpret_cast<u32*>(&tabs[blockIdx.x * 32 + who]);
-    if (built & 1u) for (u32 k = lane; k < 256; k += 32) to[k] = from[k];
-    if (built & 2u) for (u32 k = lane; k < 256; k += 32) to[256 + k] = from[256 + k];
-    if (built & 4u) for (u32 k = lane; k < 128; k += 32) to[512 + k] = from[512 + k];
+  // tables in stream order; FrameTables word offsets: ll 0 (256 words), ml 256 (256), of 512 (128)
+  for (u32 t = 0; t < 3; t++) {
+    const u32 kind = t == 0 ? SEQ_LL : (t == 1 ? SEQ_OF : SEQ_ML);
+    const u32 toWord = kind == SEQ_LL ? 0u : (kind == SEQ_ML ? 256u : 512u);
+    const u32 words = kind == SEQ_OF ? 128u : 256u;
+    bool built = false;
+    if (have) built = block_setup_table(src, descs[i], c, cur, kind, stage);
+    __syncwarp();
+    u32 any = __ballot_sync(kFull, built);
+    while (any) {
+      const int who = __ffs(any) - 1;
+      any &= any - 1;
+      const u32* from = stageWords + who * kSetupStageWords;
+      u32* to = reinterpret_cast<u32*>(&tabs[blockIdx.x * 32 + who]) + toWord;
+      for (u32 k = lane; k < words; k += 32) to[k] = from[k];
+    }
+    __syncwarp();
+  }
+  if (!have) return;
+  block_setup_tail(descs[i], c, cur);
+  ctxs[i] = c;
+  if (c.blkType == BT_COMPRESSED && !c.status) {
+    if (c.litMode == LIT_HUF && c.litSize) hufList[atomicAdd(&work->hufCount, 1u)] = i;
+    if (c.nbSeq) {
+      if (splitSmall && c.llLog <= kSeqSmallLogMax && c.mlLog <= kSeqSmallLogMax) seqList[nFrames - 1 - atomicAdd(&work->seqCountS, 1u)] = i;
+      else seqList[atomicAdd(&work->seqCount, 1u)] = i;
+    }
   }
 }
 
@@ -240,15 +251,28 @@ __global__ void __launch_bounds__(32) k_huf_decode(const u8* __restrict__ src, c
 // warp-uniform number of steps (the minimum left over the active lanes), so there is no per-step
 // completion test. A lane that finishes its frame pulls the next one from the work list and the
 // warp copies that frame's tables in cooperatively.
-constexpr u32 kSeqSlots = 88;          // frames resident per CTA: 88 x 2560 B + LUTs = 220.5 KiB of the SM's 227 KiB
-constexpr u32 kSeqThreads = 96;        // three warps; lanes 88..95 idle
-constexpr u32 kSeqWarpSmem = kSeqSlots * kSeqSlotEntries * sizeof(CSym) + 128 * sizeof(u32) + kRingWords * kSeqThreads * sizeof(u32);
-static_assert(kSeqWarpSmem <= 227 * 1024, "k_seq_decode shared memory");
+// Two geometries: the general one holds full-size tables (LL 512 + ML 512 + OF 256 entries = 2.5 KiB per frame:
+// 88 frames per SM, three warps); the small one serves frames whose LL and ML table logs are at most 8 — every frame
+// of fewer than 2048 sequences, i.e. 16 KiB frames (FSE_optimalTableLog, zstd/compress/fse_compress.c:325-342) — with
+// 3 x 256 entries = 1.5 KiB per frame: 144 frames per SM, five warps. k_block_setup sorts the frames into the two
+// work lists (the small list grows from the back of the same array).
+template <bool SMALL>
+struct SeqGeom {
+  static constexpr u32 kLL = SMALL ? 256 : 512, kML = SMALL ? 256 : 512, kOF = 256;
+  static constexpr u32 kEntries = kLL + kML + kOF;
+  static constexpr u32 kSlots = SMALL ? 144 : 88;
+  static constexpr u32 kThreads = SMALL ? 160 : 96;  // lanes >= kSlots idle
+  static constexpr u32 kSmem = kSlots * kEntries * sizeof(CSym) + 128 * sizeof(u32) + kRingWords * kThreads * sizeof(u32);
+};
+static_assert(SeqGeom<false>::kSmem <= 227 * 1024 && SeqGeom<true>::kSmem <= 227 * 1024, "k_seq_decode shared memory");
 
-__global__ void __launch_bounds__(kSeqThreads) k_seq_decode(const u8* __restrict__ src, const FrameDesc* __restrict__ descs,
+template <bool SMALL>
+__global__ void __launch_bounds__(SeqGeom<SMALL>::kThreads) k_seq_decode(const u8* __restrict__ src, const FrameDesc* __restrict__ descs,
                                                    FrameCtx* __restrict__ ctxs, const FrameTables* __restrict__ tabs,
                                                    u64* __restrict__ seqs, u32 seqStride, RoundWork* __restrict__ work,
-                                                   const u32* __restrict__ seqList) {
+                                                   const u32* __restrict__ seqList, u32 nFrames) {
+  using G = SeqGeom<SMALL>;
+  constexpr u32 kSeqSlots = G::kSlots, kSeqThreads = G::kThreads, kSeqSlotEntries = G::kEntries;
   extern __shared__ __align__(16) u8 smem[];
   CSym* slots = reinterpret_cast<CSym*>(smem);
   u32* lutLL = reinterpret_cast<u32*>(smem + kSeqSlots * kSeqSlotEntries * sizeof(CSym));
@@ -261,9 +285,9 @@ __global__ void __launch_bounds__(kSeqThreads) k_seq_decode(const u8* __restrict
   }
   __syncthreads();  // the only block-wide barrier: from here on the warps run independently
   const CSym* tLL = slots + (slot < kSeqSlots ? slot : 0) * kSeqSlotEntries;
-  const CSym* tML = tLL + 512;
-  const CSym* tOF = tLL + 1024;
-  const u32 total = work->seqCount;
+  const CSym* tML = tLL + G::kLL;
+  const CSym* tOF = tML + G::kML;
+  const u32 total = SMALL ? work->seqCountS : work->seqCount;
   bool active = false, exhausted = slot >= kSeqSlots;
   u32 frame = kNone;
   SeqState st;
@@ -274,8 +298,8 @@ __global__ void __launch_bounds__(kSeqThreads) k_seq_decode(const u8* __restrict
     if (__any_sync(kFull, !active && !exhausted)) {
       u32 f = kNone;
       if (!active && !exhausted) {
-        u32 k = atomicAdd(&work->seqNext, 1u);
-        if (k < total) f = seqList[k];
+        u32 k = atomicAdd(SMALL ? &work->seqNextS : &work->seqNext, 1u);
+        if (k < total) f = seqList[SMALL ? nFrames - 1 - k : k];
         else exhausted = true;
       }
       u32 got = __ballot_sync(kFull, f != kNone);
@@ -283,10 +307,16 @@ __global__ void __launch_bounds__(kSeqThreads) k_seq_decode(const u8* __restrict
         int who = __ffs(got) - 1;
         got &= got - 1;
         u32 wf = __shfl_sync(kFull, f, who);
+        // FrameTables keeps full-size arrays (ll at 0, ml at 1 KiB, of at 2 KiB); a slot holds the first kLL / kML / kOF
+        // entries of each, back to back (16 bytes = 8 entries per vector)
         const uint4* g = reinterpret_cast<const uint4*>(&tabs[wf]);
         uint4* d = reinterpret_cast<uint4*>(slots + (slotBase + who) * kSeqSlotEntries);
 #pragma unroll
-        for (u32 k = 0; k < kSeqSlotEntries * sizeof(CSym) / 16 / 32; k++) d[lane + 32 * k] = __ldg(g + lane + 32 * k);
+        for (u32 k = 0; k < kSeqSlotEntries / 8 / 32; k++) {
+          const u32 v = lane + 32 * k;  // vector index inside the slot
+          const u32 from = v < G::kLL / 8 ? v : (v < (G::kLL + G::kML) / 8 ? 64 + (v - G::kLL / 8) : 128 + (v - (G::kLL + G::kML) / 8));
+          d[v] = __ldg(g + from);
+        }
       }
       __syncwarp();
       if (f != kNone) {
@@ -755,7 +785,8 @@ static int sm_count() {
 
 static void configure_kernels() {
   // per device; cheap enough to repeat on every launch sequence
-  cudaFuncSetAttribute(k_seq_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSeqWarpSmem);
+  cudaFuncSetAttribute(k_seq_decode<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SeqGeom<false>::kSmem);
+  cudaFuncSetAttribute(k_seq_decode<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SeqGeom<true>::kSmem);
   cudaFuncSetAttribute(k_huf_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHufWarpSmem);
   cudaFuncSetAttribute(k_block_setup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSetupSmem);
 }
@@ -818,16 +849,23 @@ void launch_decode_rounds(const void* src, void* dst, u32 nFrames, u32 rounds, b
   // Tried and measured slower (profiles/r01i): running the Huffman stage on a side stream beside the sequence stage
   // (with 78 / 72 / 64 slots to leave it shared memory): the Huffman warps take issue slots and shared-memory
   // bandwidth from the latency-critical sequence warps (6.43 -> 6.9 .. 7.8 ms per step).
-  const u32 seqCtas = sms < div_up(nFrames, kSeqSlots) ? sms : div_up(nFrames, kSeqSlots);
+  const u32 seqCtas = sms < div_up(nFrames, SeqGeom<false>::kSlots) ? sms : div_up(nFrames, SeqGeom<false>::kSlots);
+  const u32 seqCtasS = sms < div_up(nFrames, SeqGeom<true>::kSlots) ? sms : div_up(nFrames, SeqGeom<true>::kSlots);
+  // frames of at most 32 KiB have fewer than 2048 sequences per block far more often than not: they get the small
+  // geometry first and the general kernel only sweeps up what did not qualify (usually nothing: its CTAs exit at once)
+  static const bool noSmall = getenv("ZRA_B200_NO_SMALL_SEQ") != nullptr;
+  const u32 splitSmall = (lay.litStride <= (32u << 10) && !noSmall) ? 1u : 0u;
   for (u32 r = 0; r < rounds; r++) {
     cudaMemsetAsync(work, 0, sizeof(RoundWork), st);
     ZRA_MARK(K_START);
     k_block_setup<<<div_up(nFrames, 32), 32, kSetupSmem, st>>>(in, descs, ctxs, tabs, nFrames, (first && r == 0) ? 1u : 0u, work, hufList,
-                                                               seqList);
+                                                               seqList, splitSmall);
     ZRA_MARK(K_BLOCK_SETUP);
     k_huf_decode<<<hufWarps, 32, kHufWarpSmem, st>>>(in, descs, ctxs, tabs, lit, lay.litStride, work, hufList);
     ZRA_MARK(K_HUF_DECODE);
-    k_seq_decode<<<seqCtas, kSeqThreads, kSeqWarpSmem, st>>>(in, descs, ctxs, tabs, seqs, lay.seqStride, work, seqList);
+    if (splitSmall)
+      k_seq_decode<true><<<seqCtasS, SeqGeom<true>::kThreads, SeqGeom<true>::kSmem, st>>>(in, descs, ctxs, tabs, seqs, lay.seqStride, work, seqList, nFrames);
+    k_seq_decode<false><<<seqCtas, SeqGeom<false>::kThreads, SeqGeom<false>::kSmem, st>>>(in, descs, ctxs, tabs, seqs, lay.seqStride, work, seqList, nFrames);
     ZRA_MARK(K_SEQ_DECODE);
     k_seq_execute<<<div_up((u64)nFrames * 32, kExecWarps * 32), kExecWarps * 32, 0, st>>>(in, static_cast<u8*>(dst), descs, ctxs, lit, lay.litStride, seqs,
                                                                  lay.seqStride, nFrames);
