@@ -523,6 +523,8 @@ __global__ void __launch_bounds__(kExecWarps * 32, 4) k_seq_execute(const u8* __
   const u32 nbSeq = c.nbSeq;
   u8* blk = frame + blkDst;  // block-relative positions (the records' outEnd) index this
   u64 carry = 0;  // record of the last sequence of the previous iteration
+  u32 pend = 0;   // bytes of the last tile group's partial final vector, kept in tile[0, pend) (warp-uniform)
+  u8* pendG = nullptr;  // where they belong in the output buffer
   // lanes past the end repeat the last record (ll = ml = 0); the next group's records are requested a
   // whole iteration ahead
   u64 sNext = nbSeq ? __ldg(sq + (lane < nbSeq ? lane : nbSeq - 1)) : 0ull;
@@ -543,9 +545,13 @@ __global__ void __launch_bounds__(kExecWarps * 32, 4) k_seq_execute(const u8* __
     const u32 off = rec_off(s);
     const bool viaTile = S <= kTileBytes && !__any_sync(kFull, ll >= kShortMax || ml >= kShortMax);
     if (viaTile) {
-      // tile byte t <-> block byte S0 - a + t, a = 16-byte phase of the group's first output byte
+      // tile byte t <-> block byte S0 - a + t, a = 16-byte phase of the group's first output byte. The bytes of the
+      // LAST, partial 16-byte vector of a group are not stored: they stay in the tile and become tile[0, a) of the
+      // next group (`pend` of them, then a == pend), so that groups leave as whole 16-byte vectors only.
       const u32 a = (u32)(reinterpret_cast<uintptr_t>(blk + S0) & 15u);
       u8* gbase = blk + ((i32)S0 - (i32)a);  // 16-byte aligned; tile byte t is gbase[t]
+      const bool headValid = pend != 0;      // tile[0, a) holds the carried bytes (not yet in the output buffer)
+      const i32 lowT = headValid ? 0 : (i32)a;  // tile offsets from here on are in the tile, below it in the output buffer
       const u32 tl = po - S0 + a;  // tile offset of this lane's literals
       const u32 tm = tl + ll;      // ... and of its match
       // ---- literals
@@ -555,7 +561,7 @@ __global__ void __launch_bounds__(kExecWarps * 32, 4) k_seq_execute(const u8* __
         else lanes_copy_xs(tileS + tl, litp + pl, ll, m);
       }
       __syncwarp();
-      // ---- matches: source offset relative to the tile; below `a` = already in the output buffer
+      // ---- matches: source offset relative to the tile
       const i32 ms = (i32)tm - (i32)off;
       bool pending = ml > 0;
       for (;;) {
@@ -566,7 +572,7 @@ __global__ void __launch_bounds__(kExecWarps * 32, 4) k_seq_execute(const u8* __
         const bool ready = pending && ((int)lane == first || ms + (i32)ml <= hwm);
         // one lock-step loop serves every ready lane whose source is entirely in the output buffer
         // or entirely in the tile (generic addresses); the rare rest is done after it
-        const bool inTile = ms >= (i32)a, inOut = ms + (i32)ml <= (i32)a;
+        const bool inTile = ms >= lowT, inOut = ms + (i32)ml <= lowT;
         const bool plain = ready && off >= ml && (inTile || inOut);
         const u8* sp = inTile ? tile + ms : gbase + ms;
         const u32 n = plain ? ml : 0;
@@ -576,30 +582,41 @@ __global__ void __launch_bounds__(kExecWarps * 32, 4) k_seq_execute(const u8* __
           // straddles the tile start and / or overlaps its own output: byte-serial
           for (u32 i = 0; i < ml; i++) {
             const i32 t = ms + (i32)i;
-            tile[tm + i] = t < (i32)a ? gbase[t] : tile[t];
+            tile[tm + i] = t < lowT ? gbase[t] : tile[t];
           }
         }
         if (ready) pending = false;
         __syncwarp();
       }
-      // ---- the group leaves: aligned 16-byte stores, bytes at the ragged ends
+      // ---- the group leaves: whole 16-byte vectors [firstFull, endA); the ragged start is written by bytes only when
+      // no head was carried in (first tile group of a block, or after a direct group)
       {
-        u8* g = gbase;
-        const u32 end = a + S;
-        for (u32 v = lane; v * 16 < end; v += 32) {
-          const u32 lo = v * 16, hi = lo + 16;
-          if (lo >= a && hi <= end) {
-            *reinterpret_cast<uint4*>(g + lo) = *reinterpret_cast<const uint4*>(tile + lo);
-          } else {
-            const u32 b0 = lo > a ? lo : a, b1 = hi < end ? hi : end;
-            for (u32 i = b0; i < b1; i++) g[i] = tile[i];
-          }
+        const u32 end = a + S, endA = end & ~15u;
+        const u32 firstFull = headValid ? 0u : (a + 15u) & ~15u;
+        if (!headValid && a) {
+          const u32 i = a + lane, stop = firstFull < end ? firstFull : end;
+          if (i < stop) gbase[i] = tile[i];
         }
+        for (u32 lo = firstFull + 16u * lane; lo < endA; lo += 512u)
+          *reinterpret_cast<uint4*>(gbase + lo) = *reinterpret_cast<const uint4*>(tile + lo);
+        // the partial last vector is carried if this warp owns it from its first byte
+        const u32 newPend = (end > endA && endA >= firstFull) ? end - endA : 0u;
+        u8 keep = 0;
+        if (lane < newPend) keep = tile[endA + lane];
+        __syncwarp();
+        if (lane < newPend) tile[lane] = keep;
+        pend = newPend;
+        pendG = gbase + endA;
       }
       __syncwarp();
       continue;
     }
-    // ---- direct path (long runs / matches): straight to the output buffer
+    // ---- direct path (long runs / matches): straight to the output buffer, after the carried bytes
+    if (pend) {
+      if (lane < pend) pendG[lane] = tile[lane];
+      pend = 0;
+      __syncwarp();
+    }
     const u32 myDst = blkDst + po;
     u32 longLit = __ballot_sync(kFull, ll >= kLongCopy);
     while (longLit) {
@@ -657,6 +674,10 @@ __global__ void __launch_bounds__(kExecWarps * 32, 4) k_seq_execute(const u8* __
       }
       __syncwarp();
     }
+  }
+  if (pend) {
+    if (lane < pend) pendG[lane] = tile[lane];
+    __syncwarp();
   }
   // trailing literals
   const u32 litPos = rec_lit_end(carry);
