@@ -36,6 +36,12 @@ GpuContext::GpuContext(int device) {
     }
   }
   if (check(cudaEventCreateWithFlags(&forkEvent_, cudaEventDisableTiming), "cudaEventCreate")) return;
+  {
+    int least = 0, greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&least, &greatest);
+    if (check(cudaStreamCreateWithPriority(&upStream_, cudaStreamNonBlocking, greatest), "cudaStreamCreate")) return;
+    if (check(cudaStreamCreateWithPriority(&downStream_, cudaStreamNonBlocking, greatest), "cudaStreamCreate")) return;
+  }
   if (check(cudaMallocHost(&summaryHost_, sizeof(uint32_t) * 4 * kMaxChunks), "cudaMallocHost")) return;
   ok_ = true;
 }
@@ -49,11 +55,26 @@ GpuContext::~GpuContext() {
   for (auto& s : pool_)
     if (s) cudaStreamDestroy(s);
   if (forkEvent_) cudaEventDestroy(forkEvent_);
+  for (cudaEvent_t e : upEvents_) cudaEventDestroy(e);
+  for (cudaEvent_t e : doneEvents_) cudaEventDestroy(e);
+  if (upStream_) cudaStreamDestroy(upStream_);
+  if (downStream_) cudaStreamDestroy(downStream_);
   if (summaryHost_) cudaFreeHost(summaryHost_);
   if (stream_) cudaStreamDestroy(stream_);
 }
 
 void GpuContext::bind() { cudaSetDevice(device_); }
+
+bool GpuContext::ensure_events(size_t n) {
+  while (upEvents_.size() < n) {
+    cudaEvent_t a = nullptr, b = nullptr;
+    if (check(cudaEventCreateWithFlags(&a, cudaEventDisableTiming), "cudaEventCreate")) return false;
+    upEvents_.push_back(a);
+    if (check(cudaEventCreateWithFlags(&b, cudaEventDisableTiming), "cudaEventCreate")) return false;
+    doneEvents_.push_back(b);
+  }
+  return true;
+}
 
 bool GpuContext::check(cudaError_t e, const char* what) {
   if (e == cudaSuccess) return false;
@@ -120,6 +141,7 @@ namespace {
     DecodeLayout lay;
     uint8_t* scratch;
     cudaStream_t st;
+    uint32_t idx;
     uint32_t* summary;  // pinned host words
   };
 }  // namespace
@@ -182,6 +204,7 @@ DecodeResult GpuContext::decode(const void* dSrc, size_t srcSize, const HostFram
       chunks[i].scratch = base + off;
       off += decode_scratch_bytes(chunks[i].n, maxDstCap, &tmp);
       chunks[i].st = single ? st : pool_[i % kPoolStreams];
+      chunks[i].idx = (uint32_t)i;
       chunks[i].summary = summaryHost_ + 4 * i;
     }
     // ---- fork: the pool streams start after whatever the caller queued on `st`
@@ -189,13 +212,21 @@ DecodeResult GpuContext::decode(const void* dSrc, size_t srcSize, const HostFram
       if (check(cudaEventRecord(forkEvent_, st), "fork event")) return fail_cuda();
       for (int i = 0; i < kPoolStreams && i < (int)chunks.size(); i++)
         if (check(cudaStreamWaitEvent(pool_[i], forkEvent_, 0), "fork wait")) return fail_cuda();
+      if (hostIo && (check(cudaStreamWaitEvent(upStream_, forkEvent_, 0), "fork wait") || !ensure_events(chunks.size()))) return fail_cuda();
     }
     // ---- enqueue every chunk: [H2D] -> descriptors -> rounds -> finish -> summary [-> D2H]
+    // Copies normally ride on the chunks' own streams (the copy engines take them in issue order). Putting all uploads
+    // and all downloads on two dedicated streams in chunk order was measured equal at 4 chunks and slower beyond
+    // (profiles/r01q); it stays selectable for experiments. The host path is link-bound: 1 GiB out + 0.33 GiB in
+    // take 24.2 ms (44.4 GB/s) against 56 GB/s one-way / 49.7 GB/s duplex measured on the same box (profiles/r01r).
+    static const bool orderedEnv = getenv("ZRA_B200_ORDERED_IO") != nullptr;
+    const bool ordered = hostIo && !single && orderedEnv;
     auto enqueue_tail = [&](Chunk& c) -> bool {
       launch_frame_finish(dSrc, dDst, c.n, c.scratch, c.lay, c.st, tm);
       launches_ += 1;
       if (check(cudaMemcpyAsync(c.summary, c.scratch + c.lay.offSummary, 16, cudaMemcpyDeviceToHost, c.st), "summary readback"))
         return false;
+      if (ordered && check(cudaEventRecord(doneEvents_[c.idx], c.st), "chunk done event")) return false;
       return true;
     };
     // output download of one chunk (second pass: with pageable host memory cudaMemcpyAsync blocks the
@@ -206,24 +237,31 @@ DecodeResult GpuContext::decode(const void* dSrc, size_t srcSize, const HostFram
       const HostFrame& b = frames[c.f0 + c.n - 1];
       uint64_t lo = std::max<uint64_t>(a.dstOff, io->dstSkip);
       uint64_t hi = std::min<uint64_t>(b.dstOff + b.dstCap, io->dstSize == ~0ull ? ~0ull : io->dstSkip + io->dstSize);
-      return !(hi > lo && check(cudaMemcpyAsync(io->hostDst + (lo - io->dstSkip), static_cast<const uint8_t*>(dDst) + lo, hi - lo,
-                                                cudaMemcpyDeviceToHost, c.st), "output download"));
+      if (hi <= lo) return true;
+      if (ordered && check(cudaStreamWaitEvent(downStream_, doneEvents_[c.idx], 0), "download wait")) return false;
+      return !check(cudaMemcpyAsync(io->hostDst + (lo - io->dstSkip), static_cast<const uint8_t*>(dDst) + lo, hi - lo,
+                                    cudaMemcpyDeviceToHost, ordered ? downStream_ : c.st), "output download");
     };
     for (Chunk& c : chunks) {
       launch_summary_reset(c.scratch, c.lay, c.st);
       if (frames) {
+        // `frames` may also be a DEVICE array (batched random access builds its descriptors on the GPU). The
+        // descriptors go first: from pageable host memory this copy blocks the host until everything queued on the
+        // stream before it is done, which must not be the chunk's source upload.
+        if (check(cudaMemcpyAsync(c.scratch + c.lay.offDescs, frames + c.f0, sizeof(HostFrame) * (size_t)c.n, cudaMemcpyDefault,
+                                  c.st), "descriptor upload"))
+          return fail_cuda();
         if (io && io->hostSrc) {
           const HostFrame& a = frames[c.f0];
           const HostFrame& b = frames[c.f0 + c.n - 1];
           uint64_t lo = a.srcOff, hi = b.srcOff + b.srcLen;
           if (hi > lo && check(cudaMemcpyAsync(const_cast<uint8_t*>(static_cast<const uint8_t*>(dSrc)) + lo, io->hostSrc + lo, hi - lo,
-                                               cudaMemcpyHostToDevice, c.st), "source upload"))
+                                               cudaMemcpyHostToDevice, ordered ? upStream_ : c.st), "source upload"))
+            return fail_cuda();
+          if (ordered && (check(cudaEventRecord(upEvents_[c.idx], upStream_), "upload event") ||
+                          check(cudaStreamWaitEvent(c.st, upEvents_[c.idx], 0), "upload wait")))
             return fail_cuda();
         }
-        // `frames` may also be a DEVICE array (batched random access builds its descriptors on the GPU)
-        if (check(cudaMemcpyAsync(c.scratch + c.lay.offDescs, frames + c.f0, sizeof(HostFrame) * (size_t)c.n, cudaMemcpyDefault,
-                                  c.st), "descriptor upload"))
-          return fail_cuda();
       } else {
         launch_build_descs(dSrc, 38ull + info->metaSize, info->headerSize, srcSize, info->uncompressedSize, info->frameSize,
                            (uint32_t)(firstFrame + c.f0), c.n, firstFrame * info->frameSize, c.scratch, c.lay, c.st, tm);
@@ -255,13 +293,14 @@ DecodeResult GpuContext::decode(const void* dSrc, size_t srcSize, const HostFram
         extra = true;
       }
       if (extra && c.summary[0] == 0xFFFFFFFFu &&
-          (!enqueue_download(c) || check(cudaStreamSynchronize(c.st), "output download")))
+          (!enqueue_download(c) || check(cudaStreamSynchronize(ordered ? downStream_ : c.st), "output download")))
         return fail_cuda();
       if (c.summary[0] != 0xFFFFFFFFu) {
         uint32_t code = 0;
         size_t o = c.lay.offCtxs + (size_t)c.summary[0] * frame_ctx_size() + frame_status_offset();
         if (check(cudaMemcpy(&code, c.scratch + o, 4, cudaMemcpyDeviceToHost), "status readback")) return fail_cuda();
         for (Chunk& rest : chunks) cudaStreamSynchronize(rest.st);
+        if (ordered) cudaStreamSynchronize(downStream_);
         res.zstd = (int)code;
         res.failedFrame = (uint32_t)(c.f0 + c.summary[0]);
         return res;
@@ -277,6 +316,7 @@ DecodeResult GpuContext::decode(const void* dSrc, size_t srcSize, const HostFram
         }
       }
     }
+    if (ordered && check(cudaStreamSynchronize(downStream_), "output download")) return fail_cuda();
   }
   return res;
 }

@@ -8,6 +8,7 @@
 
 #include <cstdint>
 #include <string>
+#include <vector>
 
 #include "decode_launch.h"
 #include "ra_launch.h"
@@ -120,6 +121,11 @@ class GpuContext {
   static constexpr int kPoolStreams = 16;
   cudaStream_t pool_[kPoolStreams] = {};
   cudaEvent_t forkEvent_{nullptr};
+  // host-pointer calls: every upload goes through upStream_ and every download through downStream_, in chunk order
+  // (copies issued on the chunks' own streams share the link and all finish late, which delays the first download)
+  cudaStream_t upStream_{nullptr}, downStream_{nullptr};
+  std::vector<cudaEvent_t> upEvents_, doneEvents_;
+  bool ensure_events(size_t n);
   uint32_t* summaryHost_{nullptr};  // pinned, 4 words per chunk
   uint32_t* raHost_{nullptr};       // pinned, {unique frames, first bad request}
   uint64_t raSlotFrames_{0};        // entries of raSlotOf that are initialised to "empty"
