@@ -60,6 +60,7 @@ GpuContext::~GpuContext() {
   if (upStream_) cudaStreamDestroy(upStream_);
   if (downStream_) cudaStreamDestroy(downStream_);
   if (summaryHost_) cudaFreeHost(summaryHost_);
+  if (pinnedStage_) cudaFreeHost(pinnedStage_);
   if (stream_) cudaStreamDestroy(stream_);
 }
 
@@ -102,6 +103,25 @@ void* GpuContext::ensure(DevBuf& b, size_t bytes) {
   }
   b.cap = want;
   return b.p;
+}
+
+uint8_t* GpuContext::pinned_stage(size_t bytes) {
+  if (bytes <= pinnedStageCap_ && pinnedStage_) return pinnedStage_;
+  bind();
+  if (pinnedStage_) {
+    cudaFreeHost(pinnedStage_);
+    pinnedStage_ = nullptr;
+    pinnedStageCap_ = 0;
+  }
+  size_t want = std::max<size_t>(bytes + bytes / 4, 1 << 20);
+  void* p = nullptr;
+  if (check(cudaMallocHost(&p, want), "cudaMallocHost")) {
+    want = std::max<size_t>(bytes, 1);
+    if (check(cudaMallocHost(&p, want), "cudaMallocHost")) return nullptr;
+  }
+  pinnedStage_ = static_cast<uint8_t*>(p);
+  pinnedStageCap_ = want;
+  return pinnedStage_;
 }
 
 static size_t scratch_budget() {

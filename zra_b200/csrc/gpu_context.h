@@ -66,6 +66,9 @@ class GpuContext {
 
   // Grow-only device buffers.
   void* ensure(DevBuf& b, size_t bytes);
+  // Page-locked host staging that the streaming classes hand to the user's read callback, so that the compressed
+  // bytes land where the upload can start from at link speed (grown geometrically, kept for the context's lifetime).
+  uint8_t* pinned_stage(size_t bytes);
   DevBuf scratch, stageIn, stageOut, misc;
   DevBuf raSlotOf, raUnique, raDescs, raFrames;  // batched random access (ra_context.cu)
 
@@ -127,6 +130,8 @@ class GpuContext {
   std::vector<cudaEvent_t> upEvents_, doneEvents_;
   bool ensure_events(size_t n);
   uint32_t* summaryHost_{nullptr};  // pinned, 4 words per chunk
+  uint8_t* pinnedStage_{nullptr};
+  size_t pinnedStageCap_{0};
   uint32_t* raHost_{nullptr};       // pinned, {unique frames, first bad request}
   uint64_t raSlotFrames_{0};        // entries of raSlotOf that are initialised to "empty"
   static constexpr uint32_t kMaxChunks = 1024;

@@ -309,14 +309,16 @@ namespace zra {
     u64 a = entry_get(seekTable.data(), first), b = entry_get(seekTable.data(), last);
     size_t compressedSize = b - a;
 
-    std::optional<Buffer> big;
-    if (compressedSize > maxCacheSize) big.emplace(compressedSize);
-    Buffer& input = big ? *big : cache;
-    input.resize(compressedSize);
-    readFunction(header.size + a, compressedSize, input.data());
+    // The reference reads into `cache` (or a one-off buffer above maxCacheSize, zra.cpp:383-389); here the callback —
+    // still exactly one call, on the caller's thread — fills page-locked staging owned by the GPU context, so the
+    // upload runs at link speed and no host buffer is zero-filled per request. `cache` stays for the class layout.
+    GpuContext* g = gpu();
+    u8* input = g->pinned_stage(compressedSize);
+    std::optional<Buffer> fallback;
+    if (!input) { fallback.emplace(compressedSize); input = fallback->data(); }
+    readFunction(header.size + a, compressedSize, input);
     if (first == last) return;
 
-    GpuContext* g = gpu();
     std::vector<HostFrame> frames(last - first);
     for (u64 f = first; f < last; f++) {
       HostFrame& d = frames[f - first];
@@ -329,7 +331,7 @@ namespace zra {
       d.exact = 1;
       d.pad = 0;
     }
-    raise(host_decode_frames(g, input.data(), input.size(), frames.data(), frames.size(), header.frameSize, r, size, output.data), g);
+    raise(host_decode_frames(g, input, compressedSize, frames.data(), frames.size(), header.frameSize, r, size, output.data), g);
   }
 
   void Decompressor::Decompress(size_t offset, size_t size, Buffer& output) {
@@ -358,12 +360,15 @@ namespace zra {
     size_t cur = static_cast<size_t>(reinterpret_cast<u8*>(entry) - seekTable.data()) / kEntrySize;
     size_t lastIdx = std::min(entries ? entries - 1 : 0, cur + output.size / header.frameSize);
     u64 a = entry_get(seekTable.data(), cur), b = entry_get(seekTable.data(), lastIdx);
-    cache.resize(b - a);
-    readFunction(header.size + a, cache.size(), cache.data());
+    // one read callback per call, like the reference (zra.cpp:431-433), but into page-locked staging (see Decompressor)
+    GpuContext* g = gpu();
+    const size_t compressedSize = b - a;
+    u8* input = g->pinned_stage(compressedSize);
+    if (!input) { cache.resize(compressedSize); input = cache.data(); }
+    readFunction(header.size + a, compressedSize, input);
     entry = reinterpret_cast<Entry*>(seekTable.data() + kEntrySize * lastIdx);
     if (lastIdx == cur) return 0;
 
-    GpuContext* g = gpu();
     std::vector<HostFrame> frames(lastIdx - cur);
     size_t total = 0;
     for (size_t f = cur; f < lastIdx; f++) {
@@ -378,7 +383,7 @@ namespace zra {
       d.pad = 0;
       total += d.dstCap;
     }
-    raise(host_decode_frames(g, cache.data(), cache.size(), frames.data(), frames.size(), header.frameSize, 0, total, output.data), g);
+    raise(host_decode_frames(g, input, compressedSize, frames.data(), frames.size(), header.frameSize, 0, total, output.data), g);
     return total;
   }
 }  // namespace zra
