@@ -494,6 +494,11 @@ def run_gpu(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (zra-b200 has no CPU path)"
     torch.cuda.set_device(local)
+    # rank 0's stdout carries exactly ONE JSON line: whatever native libraries print on fd 1 in the meantime
+    # (NCCL's version banner, for one) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -706,9 +711,13 @@ def run_gpu(args):
                                                           "sample": "zra::DecompressBuffer, faithful single-thread reference"}}
             except Exception as e:  # the baseline must never take the GPU numbers down with it
                 line["cpu_baseline"] = {"value": None, "unit": "GB/s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(json_fd, 1)
+    os.close(json_fd)
 
 
 def main():
