@@ -35,6 +35,33 @@ def to_device(torch, a, slack=16):
     return t
 
 
+# ------------------------------------------------------------------ frame-range shards (what each rank of a box runs)
+@pytest.mark.parametrize("name,shards", [("text_f16384_l3", 3), ("text_f262144_l3", 2), ("mixed_f16384_l3", 8), ("onebyte_f16384_l3", 2),
+                                         ("text_f1000_l5", 5)])
+def test_frame_range_shards_concatenate_to_the_whole(torch_cuda, ctx, name, shards):
+    """ZraCudaDecompressFrames over contiguous frame ranges [g*F/G, (g+1)*F/G) regenerates, shard by shard,
+    exactly the bytes of the whole archive; every shard writes only its own range."""
+    from zra_b200 import shard
+
+    torch = torch_cuda
+    archive, meta = golden_archive(name)
+    h = parse_header(archive)
+    frames = h["tableSize"] - 1
+    fs = h["frameSize"]
+    d_in = to_device(torch, archive)
+    got = np.zeros(meta["bytes"], np.uint8)
+    for g in range(shards):
+        f0, f1 = shard.frame_range(frames, g, shards)
+        lo, hi = min(f0 * fs, meta["bytes"]), min(f1 * fs, meta["bytes"])
+        d_out = torch.full((hi - lo + 64,), 0x55, dtype=torch.uint8, device="cuda")
+        ctx.decompress_frames(d_in.data_ptr(), archive.size, f0, f1 - f0, d_out.data_ptr(), hi - lo, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        host = d_out.cpu().numpy()
+        assert (host[hi - lo:] == 0x55).all()
+        got[lo:hi] = host[: hi - lo]
+    assert sha(got) == meta["sha256"]
+
+
 # ------------------------------------------------------------------ golden vectors
 @pytest.mark.parametrize("name", golden_archives())
 def test_golden_archives_host_api(name):
