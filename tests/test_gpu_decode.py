@@ -294,3 +294,45 @@ def test_reference_archives_roundtrip(torch_cuda, ctx, kind, fs, lvl, ck, n):
     d_part = torch.zeros(hi - lo, dtype=torch.uint8, device="cuda")
     ctx.decompress_frames(d_in.data_ptr(), z.size, f0, cnt, d_part.data_ptr(), hi - lo, torch.cuda.current_stream().cuda_stream)
     assert torch.equal(d_part, torch.from_numpy(data[lo:hi]).cuda())
+
+
+# ------------------------------------------------------------------ scratch budget: archives larger than one group
+@needs_ref
+@pytest.mark.parametrize("fs,env", [(16384, {"ZRA_B200_SCRATCH_MB": "64", "ZRA_B200_CHUNKS": "3"}),
+                                    (262144, {"ZRA_B200_SCRATCH_MB": "64", "ZRA_B200_CHUNKS": "7"}),
+                                    (65536, {"ZRA_B200_CHUNKS": "40"})])
+def test_group_and_chunk_cuts_do_not_change_the_result(tmp_path, fs, env):
+    """BASELINE's full sizes (8 GiB shards) do not fit one scratch group: the decode then runs group after group, each
+    cut into chunks. Forced here at a small size through the tuning environment (read once per process, hence the
+    subprocess): device path, host path and batched random access must give the reference's bytes."""
+    import os
+    import subprocess
+    import sys
+
+    n = 48 << 20
+    data = synth.text(n, seed=fs)
+    archive = refzra.ref_compress_mt(data, 3, fs, True)
+    np.asarray(archive).tofile(tmp_path / "a.zra")
+    data.tofile(tmp_path / "a.bin")
+    code = f"""
+import sys, numpy as np, torch
+sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})
+import zra_b200
+a = np.fromfile({str(tmp_path / 'a.zra')!r}, dtype=np.uint8); d = np.fromfile({str(tmp_path / 'a.bin')!r}, dtype=np.uint8)
+assert np.array_equal(zra_b200.DecompressBuffer(a), d), "host path"
+ctx = zra_b200.CudaContext(0)
+d_in = torch.zeros(a.size + 64, dtype=torch.uint8, device="cuda"); d_in[:a.size] = torch.from_numpy(a).cuda()
+d_out = torch.empty(d.size, dtype=torch.uint8, device="cuda")
+ctx.decompress_buffer(d_in.data_ptr(), a.size, d_out.data_ptr(), d.size, torch.cuda.current_stream().cuda_stream)
+torch.cuda.synchronize()
+assert np.array_equal(d_out.cpu().numpy(), d), "device path"
+rng = np.random.default_rng(5); offs = rng.integers(0, d.size - 4097, 4096).astype(np.uint64)
+d_off = torch.from_numpy(offs.view(np.int64)).cuda(); d_ra = torch.empty(4096 * 4096, dtype=torch.uint8, device="cuda")
+ctx.decompress_ra_batch(d_in.data_ptr(), a.size, d_off.data_ptr(), 4096, d_ra.data_ptr(), uniform_size=4096, stream=torch.cuda.current_stream().cuda_stream)
+got = d_ra.cpu().numpy().reshape(4096, 4096)
+for i in range(0, 4096, 37): assert np.array_equal(got[i], d[int(offs[i]): int(offs[i]) + 4096]), "random access"
+print("ok")
+"""
+    r = subprocess.run([sys.executable, "-c", code], env={**os.environ, **env}, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                       text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-1500:]

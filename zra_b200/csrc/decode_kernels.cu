@@ -256,22 +256,22 @@ __global__ void __launch_bounds__(32) k_huf_decode(const u8* __restrict__ src, c
 // of fewer than 2048 sequences, i.e. 16 KiB frames (FSE_optimalTableLog, zstd/compress/fse_compress.c:325-342) — with
 // 3 x 256 entries = 1.5 KiB per frame: 144 frames per SM, five warps. k_block_setup sorts the frames into the two
 // work lists (the small list grows from the back of the same array).
-template <bool SMALL>
+template <bool SMALL, u32 SLOTS = 0>
 struct SeqGeom {
   static constexpr u32 kLL = SMALL ? 256 : 512, kML = SMALL ? 256 : 512, kOF = 256;
   static constexpr u32 kEntries = kLL + kML + kOF;
-  static constexpr u32 kSlots = SMALL ? 144 : 88;
-  static constexpr u32 kThreads = SMALL ? 160 : 96;  // lanes >= kSlots idle
+  static constexpr u32 kSlots = SLOTS ? SLOTS : (SMALL ? 144 : 88);
+  static constexpr u32 kThreads = (kSlots + 31) / 32 * 32;  // lanes >= kSlots idle
   static constexpr u32 kSmem = kSlots * kEntries * sizeof(CSym) + 128 * sizeof(u32) + kRingWords * kThreads * sizeof(u32);
 };
 static_assert(SeqGeom<false>::kSmem <= 227 * 1024 && SeqGeom<true>::kSmem <= 227 * 1024, "k_seq_decode shared memory");
 
-template <bool SMALL>
-__global__ void __launch_bounds__(SeqGeom<SMALL>::kThreads) k_seq_decode(const u8* __restrict__ src, const FrameDesc* __restrict__ descs,
+template <bool SMALL, u32 SLOTS = 0>
+__global__ void __launch_bounds__(SeqGeom<SMALL, SLOTS>::kThreads) k_seq_decode(const u8* __restrict__ src, const FrameDesc* __restrict__ descs,
                                                    FrameCtx* __restrict__ ctxs, const FrameTables* __restrict__ tabs,
                                                    u64* __restrict__ seqs, u32 seqStride, RoundWork* __restrict__ work,
                                                    const u32* __restrict__ seqList, u32 nFrames) {
-  using G = SeqGeom<SMALL>;
+  using G = SeqGeom<SMALL, SLOTS>;
   constexpr u32 kSeqSlots = G::kSlots, kSeqThreads = G::kThreads, kSeqSlotEntries = G::kEntries;
   extern __shared__ __align__(16) u8 smem[];
   CSym* slots = reinterpret_cast<CSym*>(smem);
@@ -808,6 +808,7 @@ static void configure_kernels() {
   // per device; cheap enough to repeat on every launch sequence
   cudaFuncSetAttribute(k_seq_decode<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SeqGeom<false>::kSmem);
   cudaFuncSetAttribute(k_seq_decode<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SeqGeom<true>::kSmem);
+  cudaFuncSetAttribute(k_seq_decode<false, 72>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SeqGeom<false, 72>::kSmem);
   cudaFuncSetAttribute(k_huf_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHufWarpSmem);
   cudaFuncSetAttribute(k_block_setup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSetupSmem);
 }
@@ -870,7 +871,12 @@ void launch_decode_rounds(const void* src, void* dst, u32 nFrames, u32 rounds, b
   // Tried and measured slower (profiles/r01i): running the Huffman stage on a side stream beside the sequence stage
   // (with 78 / 72 / 64 slots to leave it shared memory): the Huffman warps take issue slots and shared-memory
   // bandwidth from the latency-critical sequence warps (6.43 -> 6.9 .. 7.8 ms per step).
-  const u32 seqCtas = sms < div_up(nFrames, SeqGeom<false>::kSlots) ? sms : div_up(nFrames, SeqGeom<false>::kSlots);
+  // Chunks of more than one wave (>= 148 x 88 frames: archives of 4 GiB and up) are throughput-bound, not latency-bound:
+  // with 72 slots the sequence CTA leaves room for one execute CTA on its SM, and the two overlap (4 GiB: 174 -> 183 GB/s;
+  // at 1 GiB the same choice costs 9 %: the execute warps slow the latency-critical chains down; profiles/r01v).
+  static const u32 slotsEnv = [] { const char* e = getenv("ZRA_B200_SEQ_SLOTS"); return e ? (u32)atoi(e) : 0u; }();
+  const u32 genSlots = slotsEnv == 72 || slotsEnv == 88 ? slotsEnv : (nFrames >= sms * SeqGeom<false>::kSlots ? 72u : SeqGeom<false>::kSlots);
+  const u32 seqCtas = sms < div_up(nFrames, genSlots) ? sms : div_up(nFrames, genSlots);
   const u32 seqCtasS = sms < div_up(nFrames, SeqGeom<true>::kSlots) ? sms : div_up(nFrames, SeqGeom<true>::kSlots);
   // frames of at most 32 KiB have fewer than 2048 sequences per block far more often than not: they get the small
   // geometry first and the general kernel only sweeps up what did not qualify (usually nothing: its CTAs exit at once)
@@ -886,6 +892,8 @@ void launch_decode_rounds(const void* src, void* dst, u32 nFrames, u32 rounds, b
     ZRA_MARK(K_HUF_DECODE);
     if (splitSmall)
       k_seq_decode<true><<<seqCtasS, SeqGeom<true>::kThreads, SeqGeom<true>::kSmem, st>>>(in, descs, ctxs, tabs, seqs, lay.seqStride, work, seqList, nFrames);
+    if (genSlots == 72) k_seq_decode<false, 72><<<seqCtas, SeqGeom<false, 72>::kThreads, SeqGeom<false, 72>::kSmem, st>>>(in, descs, ctxs, tabs, seqs, lay.seqStride, work, seqList, nFrames);
+    else
     k_seq_decode<false><<<seqCtas, SeqGeom<false>::kThreads, SeqGeom<false>::kSmem, st>>>(in, descs, ctxs, tabs, seqs, lay.seqStride, work, seqList, nFrames);
     ZRA_MARK(K_SEQ_DECODE);
     k_seq_execute<<<div_up((u64)nFrames * 32, kExecWarps * 32), kExecWarps * 32, 0, st>>>(in, static_cast<u8*>(dst), descs, ctxs, lit, lay.litStride, seqs,
