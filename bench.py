@@ -559,6 +559,7 @@ def run_gpu(args):
             step()
         e1.record(stream)
         barrier()
+        launches = ctx.launch_count() - launches0
         # the timed region lasts tens of milliseconds, one nvidia-smi poll at best: keep the same load running (untimed)
         # for about a second more so that the clock / throttle samples describe this workload, not an idle GPU
         t_hold = time.perf_counter()
@@ -566,7 +567,6 @@ def run_gpu(args):
             step()
         torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    launches = ctx.launch_count() - launches0
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
