@@ -146,19 +146,22 @@ ZRA_DEV u32 match_len(const u8* base, u64 fbase, u32 a, u32 b, u32 limit) {
 // Converts (litLength, matchLength, real offset) to the wire offsetValue with the decoder's
 // repeat-offset rules and keeps the history in step with what the decoder will compute.
 ZRA_DEV u64 emit_sequence(EncCtx& c, u32 ll, u32 ml, u32 offset) {
-  u32 value;
-  u32 r0 = c.rep[0], r1 = c.rep[1], r2 = c.rep[2];
-  if (ll) {
-    if (offset == r0) value = 1;
-    else if (offset == r1) { value = 2; c.rep[1] = r0; c.rep[0] = offset; }
-    else if (offset == r2) { value = 3; c.rep[2] = r1; c.rep[1] = r0; c.rep[0] = offset; }
-    else { value = offset + 3; c.rep[2] = r1; c.rep[1] = r0; c.rep[0] = offset; }
-  } else {
-    if (offset == r1) { value = 1; c.rep[1] = r0; c.rep[0] = offset; }
-    else if (offset == r2) { value = 2; c.rep[2] = r1; c.rep[1] = r0; c.rep[0] = offset; }
-    else if (offset == r0 - 1 && r0 > 1) { value = 3; c.rep[2] = r1; c.rep[1] = r0; c.rep[0] = offset; }
-    else { value = offset + 3; c.rep[2] = r1; c.rep[1] = r0; c.rep[0] = offset; }
-  }
+  // Branch-free (this runs in the serial selection loop of the frame-cooperative matcher). With ll > 0 the wire values
+  // 1/2/3 mean rep0/rep1/rep2; with ll == 0 they mean rep1/rep2/rep0-1 (zstd_decompress_block.c:871-888).
+  const u32 r0 = c.rep[0], r1 = c.rep[1], r2 = c.rep[2];
+  const bool ll0 = ll == 0;
+  const u32 c1 = ll0 ? r1 : r0, c2 = ll0 ? r2 : r1, c3 = ll0 ? r0 - 1u : r2;
+  const bool m1 = offset == c1;
+  const bool m2 = !m1 && offset == c2;
+  const bool m3 = !m1 && !m2 && offset == c3 && !(ll0 && r0 <= 1u);
+  const u32 idx = m1 ? 1u : (m2 ? 2u : (m3 ? 3u : 0u));
+  const u32 value = idx ? idx : offset + 3u;
+  // history: rep0 itself (idx 1, ll > 0) changes nothing; rep1 (idx + ll0 == 2) swaps the first two; the rest shifts
+  const bool same = m1 && !ll0;
+  const bool keep2 = idx != 0 && idx + (ll0 ? 1u : 0u) <= 2u;
+  c.rep[2] = keep2 ? r2 : r1;
+  c.rep[1] = same ? r1 : r0;
+  c.rep[0] = offset;
   return seq_pack(ll, ml, value);
 }
 
