@@ -272,6 +272,8 @@ def test_corruption_matches_oracle():
     ("text", 262144, 3, True, (32 << 20) + 12345),
     ("mixed", 65536, 2, True, 32 << 20),
     ("text", 1 << 20, 5, True, 16 << 20),
+    ("text", 4 << 20, 1, True, (24 << 20) + 999),   # 32 blocks per frame: repeat-mode tables, treeless literals across rounds
+    ("mixed", 1 << 20, 3, False, 12 << 20),
     ("text", 3000, 9, True, 3 << 20),
     ("zeros", 65536, 3, True, 16 << 20),
 ])

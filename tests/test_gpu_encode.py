@@ -57,6 +57,7 @@ def check_archive(z, data, fs):
     ("text", 1, 16384, 0, False),
     ("text", 0, 16384, 3, True),
     ("text", 700_000, 700_000, 3, True),
+    ("text", (9 << 20) + 5, 4 << 20, 3, True),
     ("text", 300_000, 1 << 20, -5, True),
     ("text", 1 << 20, 65536, 9, True),
 ])
