@@ -176,6 +176,8 @@ __global__ void __launch_bounds__(T) k_enc_match_cta(EncJob j, EncView v) {
   u32* info = reinterpret_cast<u32*>(smem + 2ull * (nS + nL));
   u32* hist = info + T;   // 256 literal counts, then 36 + 32 + 53 code counts
   u32* cnt = hist + 256;
+  u16* take = reinterpret_cast<u16*>(cnt + 128);  // per position of the round: the match a walk arriving there takes
+  __shared__ u32 sHas[T / 32];                     // per 32 positions: which of them have a match
   const u8* base = j.in;
   const u64 fbase = j.inOff + (u64)i * j.frameSize;
   const EncScratch s = v.frame(i);
@@ -250,27 +252,40 @@ __global__ void __launch_bounds__(T) k_enc_match_cta(EncJob j, EncView v) {
       if (bestLen >= 4) e = bestOff | (bestLen << 16) | (more ? kInfoMore : 0u);
     }
     info[tid] = e;
+    {
+      const u32 bal = __ballot_sync(kFullMask, e != 0);
+      if (lane == 0) sHas[warp] = bal;
+    }
     __syncthreads();
-    // ---- C: greedy selection by warp 0
+    // ---- B2 (all threads): which match does a walk take that ARRIVES at position rb + tid? The next position at or
+    // after it that has a match, moved one byte on when that match is short (< 8) and its right neighbour's is not
+    // (the one-byte lazy step; never across a 32-position group, as in the selection loop this replaces). Doing the
+    // search here, in parallel, leaves the serial walk two shared-memory loads per sequence.
+    {
+      u32 g = warp;
+      u32 w = sHas[g] & (0xFFFFFFFFu << lane);
+      while (!w && ++g < T / 32) w = sHas[g];
+      u32 q = 0xFFFFu;
+      if (w) {
+        q = g * 32 + ((u32)__ffs((int)w) - 1);
+        if ((q & 31u) != 31u && ((sHas[q >> 5] >> ((q & 31u) + 1u)) & 1u)) {
+          const u32 l1 = (info[q] >> 16) & 0xFFu, l2 = (info[q + 1] >> 16) & 0xFFu;
+          if (l1 < 8 && l2 >= 8) q++;
+        }
+      }
+      take[tid] = (u16)q;
+    }
+    __syncthreads();
+    // ---- C: greedy walk by warp 0 (warp-uniform state; the lanes only differ in the warp-wide extension)
     if (warp == 0) {
-      for (u32 g = 0; g < T / 32; g++) {
-        const u32 gb = rb + g * 32;
-        if (gb >= hashEnd) break;
-        if (anchor >= gb + 32) continue;
-        const u32 my = info[g * 32 + lane];
-        const u32 mask = __ballot_sync(kFullMask, my != 0);
+      {
         for (;;) {
-          const u32 from = anchor > gb ? anchor - gb : 0;
-          if (from >= 32) break;
-          const u32 m = mask & (0xFFFFFFFFu << from);
-          if (!m) break;
-          u32 k = (u32)__ffs((int)m) - 1;
-          u32 ee = __shfl_sync(kFullMask, my, k);
-          if (k < 31 && ((mask >> (k + 1)) & 1u)) {
-            const u32 e2 = __shfl_sync(kFullMask, my, k + 1);
-            const u32 l1 = (ee >> 16) & 0xFFu, l2 = (e2 >> 16) & 0xFFu;
-            if (l1 < 8 && l2 >= 8) { ee = e2; k++; }
-          }
+          const u32 arrive = anchor > rb ? anchor - rb : 0;
+          if (arrive >= T) break;
+          const u32 k = take[arrive];
+          if (k == 0xFFFFu) break;
+          const u32 ee = info[k];
+          const u32 gb = rb;
           const u32 mpos = gb + k;
           u32 ml = (ee >> 16) & 0xFFu;
           const u32 off = ee & 0xFFFFu;
@@ -753,7 +768,7 @@ size_t encode_scratch_bytes(u32 nFrames, u32 frameSize, u32 lastFrameLen, int le
   lay->matchSmem = 2u * ((1u << lay->matchLogS) + (lay->matchLogL ? (1u << lay->matchLogL) : 0u));
   lay->matchThreads = lay->matchSmem > 100u * 1024u ? 512u : 256u;
   if (getenv("ZRA_B200_ENC_THREADS")) lay->matchThreads = atoi(getenv("ZRA_B200_ENC_THREADS")) >= 512 ? 512u : 256u;
-  lay->matchSmem += 4u * lay->matchThreads + 4u * (256u + 128u);
+  lay->matchSmem += 4u * lay->matchThreads + 4u * (256u + 128u) + 2u * lay->matchThreads;
   lay->ctaMatch = frameSize <= 65536u && lay->matchSmem <= 226u * 1024u && !getenv("ZRA_B200_ENC_SERIAL");
   const u32 blk = frameSize < kBlockSizeMax ? frameSize : kBlockSizeMax;
   lay->seqStride = blk / 3 + 2;
