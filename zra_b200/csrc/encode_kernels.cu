@@ -369,6 +369,245 @@ __global__ void __launch_bounds__(T) k_enc_match_cta(EncJob j, EncView v) {
   }
 }
 
+__device__ __forceinline__ void bar_sync_n(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_arrive_n(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+template <int T>
+__global__ void __launch_bounds__(T) k_enc_match_cta_pipe(EncJob j, EncView v) {
+  extern __shared__ __align__(16) u8 smem[];
+  // Producer / consumer form of k_enc_match_cta: warps 1.. (P = T - 32 threads) run the hash / insert / verify / take
+  // phases of round r + 1 while warp 0 walks round r; info[], take[] and sHas[] are double-buffered and handed over
+  // with named barriers (FULL: producers arrive, the walker waits; EMPTY: the walker arrives, producers wait before
+  // they reuse the buffer two rounds later). The round-skip test uses the anchor published after round r - 2, which the
+  // EMPTY barrier makes final, so the tables — and the archive — do not depend on timing.
+  constexpr u32 P = T - 32;
+  constexpr int BAR_PROD = 1, BAR_FULL = 2, BAR_EMPTY = 4;
+  __shared__ u32 sAnchorAfter[2];
+  __shared__ u32 sSkip[2];
+  __shared__ u32 sFinal[8];
+  const u32 i = blockIdx.x;
+  const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  EncCtx& gc = v.ctx(i);
+  const u32 len = gc.srcLen;
+  const u32 logS = v.lay.matchLogS, logL = v.lay.matchLogL, mls = v.lay.matchMls;
+  const bool dfast = logL != 0;
+  const u32 nS = 1u << logS, nL = dfast ? (1u << logL) : 0u;
+  u16* tabS = reinterpret_cast<u16*>(smem);
+  u16* tabL = tabS + nS;
+  u32* info = reinterpret_cast<u32*>(smem + 2ull * (nS + nL));
+  u32* hist = info + 2 * T;   // (info is [2][T]) 256 literal counts, then 36 + 32 + 53 code counts
+  u32* cnt = hist + 256;
+  u16* take = reinterpret_cast<u16*>(cnt + 128);  // [2][T] per position of the round: the match a walk arriving there takes
+  __shared__ u32 sHas[2][T / 32];                  // per 32 positions: which of them have a match
+  const u8* base = j.in;
+  const u64 fbase = j.inOff + (u64)i * j.frameSize;
+  const EncScratch s = v.frame(i);
+  u32* side = reinterpret_cast<u32*>(s.hufOut);  // per sequence: literal source | literal destination << 16
+  // ---- clear tables and histograms
+  {
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    const u32 n16 = (2u * (nS + nL)) >> 4;
+    for (u32 k = tid; k < n16; k += T) z[k] = make_uint4(0, 0, 0, 0);
+    for (u32 k = tid; k < 256 + 128; k += T) hist[k] = 0;
+    if (tid == 0) { sAnchorAfter[0] = sAnchorAfter[1] = 0; sSkip[0] = sSkip[1] = 0; }
+  }
+  __syncthreads();
+  // selector state (meaningful in warp 0, warp-uniform)
+  EncCtx rc;
+  rc.rep[0] = 1; rc.rep[1] = 4; rc.rep[2] = 8;
+  u32 anchor = 0, nseq = 0, litPos = 0;
+  const u32 hashEnd = len >= 16 ? len - 8 : 0;  // positions below this can start a match (zstd: ip < iend - 8)
+  const u32 rounds = hashEnd ? (hashEnd + P - 1) / P : 0;
+  if (warp != 0) {
+    const u32 ptid = tid - 32, pwarp = warp - 1;
+    for (u32 r = 0, rb = 0; r < rounds; r++, rb += P) {
+      const u32 buf = r & 1u;
+      if (r >= 2) bar_sync_n(BAR_EMPTY + buf, T);  // the walker is done with this buffer (round r - 2)
+    const u32 pos = rb + ptid;
+    const u32 curAnchor = sAnchorAfter[buf];  // the anchor after round r - 2 (final: EMPTY barrier above)
+    const bool skip = curAnchor >= rb + P;     // the whole round lies inside a match already taken (uniform)
+    if (!skip) {
+    // ---- A: hash, read the pre-round candidates, then insert. The insert keeps the LOWEST position
+    // of this round per cell (16-bit compare-and-swap on the distance from the round base, under
+    // which every older entry ranks above the round's own), so the table — and with it the archive —
+    // does not depend on thread timing, and later positions of the round see an in-round candidate.
+    const bool live = pos < hashEnd;
+    u64 x = 0;
+    u32 hS = 0, hL = 0, cS = 0, cL = 0;
+    if (live) {
+      x = gld8(base, fbase + pos);
+      hS = mls <= 4 ? ((u32)x * 2654435761u) >> (32 - logS) : (u32)(((x << (64 - 8 * mls)) * 0x9E3779B97F4A7C15ull) >> (64 - logS));
+      cS = tabS[hS];
+      if (dfast) {
+        hL = (u32)((x * 0xCF1BBCDCB7A56463ull) >> (64 - logL));
+        cL = tabL[hL];
+      }
+    }
+    bar_sync_n(BAR_PROD, P);
+    if (live) {
+      table_insert_min(&tabS[hS], pos, rb);
+      if (dfast) table_insert_min(&tabL[hL], pos, rb);
+    }
+    bar_sync_n(BAR_PROD, P);
+    u32 e = 0;
+    if (live && pos >= curAnchor && pos > 0) {
+      u32 c2 = tabS[hS];
+      if (c2 < pos && c2 >= rb) cS = c2;
+      bool okS = cS < pos, okL = false;
+      if (dfast) {
+        c2 = tabL[hL];
+        if (c2 < pos && c2 >= rb) cL = c2;
+        okL = cL < pos;
+      }
+      // ---- B: verify
+      u32 bestLen = 0, bestOff = 0;
+      u32 nL8 = 0, nS8 = 0;
+      if (okL) nL8 = common8(gld8(base, fbase + cL) ^ x);
+      if (okS && (!okL || cS != cL)) nS8 = common8(gld8(base, fbase + cS) ^ x);
+      if (nL8 >= 4 && nL8 >= nS8) { bestLen = nL8; bestOff = pos - cL; }
+      else if (nS8 >= 4) { bestLen = nS8; bestOff = pos - cS; }
+      bool more = false;
+      if (bestLen == 8) {
+        const u32 cand = pos - bestOff;
+        more = true;
+        while (bestLen < kLaneLenCap && pos + bestLen + 8 <= len) {
+          const u32 c = common8(gld8(base, fbase + pos + bestLen) ^ gld8(base, fbase + cand + bestLen));
+          bestLen += c;
+          if (c < 8) { more = false; break; }
+        }
+      }
+      if (bestLen >= 4) e = bestOff | (bestLen << 16) | (more ? kInfoMore : 0u);
+    }
+    info[buf * T + ptid] = e;
+    {
+      const u32 bal = __ballot_sync(kFullMask, e != 0);
+      if (lane == 0) sHas[buf][pwarp] = bal;
+    }
+    bar_sync_n(BAR_PROD, P);
+    // ---- B2 (all threads): which match does a walk take that ARRIVES at position rb + tid? The next position at or
+    // after it that has a match, moved one byte on when that match is short (< 8) and its right neighbour's is not
+    // (the one-byte lazy step; never across a 32-position group, as in the selection loop this replaces). Doing the
+    // search here, in parallel, leaves the serial walk two shared-memory loads per sequence.
+    {
+      u32 g = pwarp;
+      u32 w = sHas[buf][g] & (0xFFFFFFFFu << lane);
+      while (!w && ++g < P / 32) w = sHas[buf][g];
+      u32 q = 0xFFFFu;
+      if (w) {
+        q = g * 32 + ((u32)__ffs((int)w) - 1);
+        if ((q & 31u) != 31u && ((sHas[buf][q >> 5] >> ((q & 31u) + 1u)) & 1u)) {
+          const u32 l1 = (info[buf * T + q] >> 16) & 0xFFu, l2 = (info[buf * T + q + 1] >> 16) & 0xFFu;
+          if (l1 < 8 && l2 >= 8) q++;
+        }
+      }
+      take[buf * T + ptid] = (u16)q;
+    }
+    }
+      if (ptid == 0) sSkip[buf] = skip ? 1u : 0u;
+      __threadfence_block();
+      bar_arrive_n(BAR_FULL + buf, T);
+    }
+    // the walker's last arrivals (rounds whose buffers nobody reuses) are consumed here so that no barrier is left open
+    for (u32 k = rounds >= 2 ? rounds - 2 : 0; k < rounds; k++) bar_sync_n(BAR_EMPTY + (k & 1u), T);
+  } else {
+    for (u32 r = 0, rb = 0; r < rounds; r++, rb += P) {
+      const u32 buf = r & 1u;
+      bar_sync_n(BAR_FULL + buf, T);
+      if (!sSkip[buf]) {
+      {
+        for (;;) {
+          const u32 arrive = anchor > rb ? anchor - rb : 0;
+          if (arrive >= P) break;
+          const u32 k = take[buf * T + arrive];
+          if (k == 0xFFFFu) break;
+          const u32 ee = info[buf * T + k];
+          const u32 gb = rb;
+          const u32 mpos = gb + k;
+          u32 ml = (ee >> 16) & 0xFFu;
+          const u32 off = ee & 0xFFFFu;
+          if (ee & kInfoMore) {
+            // warp-wide extension: 4 bytes per lane and trip
+            for (;;) {
+              const u32 a = mpos + ml + 4 * lane;
+              u32 diff = 0;  // byte k of diff != 0: byte k differs / is past the end
+              if (a + 4 <= len) {
+                diff = gld4(base, fbase + a) ^ gld4(base, fbase + a - off);
+              } else {
+                for (u32 b = 0; b < 4; b++) {
+                  if (a + b >= len || base[fbase + a + b] != base[fbase + a + b - off]) { diff = 0xFFu << (8 * b); break; }
+                }
+              }
+              const u32 bad = __ballot_sync(kFullMask, diff != 0);
+              if (!bad) { ml += 128; continue; }
+              const u32 first = (u32)__ffs((int)bad) - 1;
+              const u32 d = __shfl_sync(kFullMask, diff, first);
+              ml += 4 * first + (((u32)__ffs((int)d) - 1) >> 3);
+              break;
+            }
+          }
+          // ---- emit
+          const u32 ll = mpos - anchor;
+          const u64 rec = emit_sequence(rc, ll, ml, off);
+          if (lane == 0) {
+            s.seqs[nseq] = rec;
+            side[nseq] = anchor | (litPos << 16);
+          }
+          nseq++;
+          litPos += ll;
+          anchor = mpos + ml;
+        }
+      }
+      }
+      if (lane == 0) sAnchorAfter[buf] = anchor;
+      __threadfence_block();
+      bar_arrive_n(BAR_EMPTY + buf, T);
+    }
+    if (lane == 0) sAnchorAfter[0] = anchor;
+  }
+  // ---- literal gather + histograms (whole CTA), results
+  if (tid == 0) {
+    sFinal[0] = litPos; sFinal[1] = nseq; sFinal[2] = rc.rep[0]; sFinal[3] = rc.rep[1]; sFinal[4] = rc.rep[2];
+    __threadfence_block();
+  }
+  __syncthreads();
+  anchor = sAnchorAfter[0];
+  litPos = sFinal[0];
+  nseq = sFinal[1];
+  __threadfence();  // the records / side entries were written by warp 0 through global memory
+  for (u32 q = tid; q < nseq; q += T) {
+    const u64 rec = s.seqs[q];
+    const u32 sd = side[q];
+    const u32 ll = seq_ll(rec), from = sd & 0xFFFFu, to = sd >> 16;
+    for (u32 k = 0; k < ll; k++) {
+      const u8 b = base[fbase + from + k];
+      s.lit[to + k] = b;
+      atomicAdd(&hist[b], 1u);
+    }
+    atomicAdd(&cnt[ll_code_fast(ll)], 1u);
+    atomicAdd(&cnt[36 + highbit32(seq_off(rec))], 1u);
+    atomicAdd(&cnt[68 + ml_code_fast(seq_ml(rec) - 3)], 1u);
+  }
+  const u32 rest = len - anchor;
+  for (u32 q = tid; q < rest; q += T) {
+    const u8 b = base[fbase + anchor + q];
+    s.lit[litPos + q] = b;
+    atomicAdd(&hist[b], 1u);
+  }
+  __syncthreads();
+  for (u32 k = tid; k < 256; k += T) s.hist[k] = hist[k];
+  for (u32 k = tid; k < 128; k += T) s.cnt[k] = cnt[k];
+  if (tid == 0) {
+    gc.blkActive = 1;
+    gc.blkPos = 0;
+    gc.blkLen = len;
+    gc.lastBlock = 1;
+    gc.repSave[0] = 1; gc.repSave[1] = 4; gc.repSave[2] = 8;
+    gc.rep[0] = sFinal[2]; gc.rep[1] = sFinal[3]; gc.rep[2] = sFinal[4];
+    gc.nbSeq = nseq;
+    gc.litSize = litPos + rest;
+  }
+}
+
 __global__ void k_enc_literals(EncJob j, EncView v) {
   u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= j.nFrames) return;
@@ -768,7 +1007,11 @@ size_t encode_scratch_bytes(u32 nFrames, u32 frameSize, u32 lastFrameLen, int le
   lay->matchSmem = 2u * ((1u << lay->matchLogS) + (lay->matchLogL ? (1u << lay->matchLogL) : 0u));
   lay->matchThreads = lay->matchSmem > 100u * 1024u ? 512u : 256u;
   if (getenv("ZRA_B200_ENC_THREADS")) lay->matchThreads = atoi(getenv("ZRA_B200_ENC_THREADS")) >= 512 ? 512u : 256u;
-  lay->matchSmem += 4u * lay->matchThreads + 4u * (256u + 128u) + 2u * lay->matchThreads;
+  // producer / consumer form: pays when few frames fit an SM (big tables: level 3 at 64 KiB, 48 KiB -> 4 CTAs per SM:
+  // 16.4 -> 20.3 GB/s text, 20.7 -> 24.4 mixed), costs ~10 % when many do (their phases already overlap across CTAs,
+  // and the walker warp takes 1/8 of the threads): profiles/r02d
+  lay->matchPipe = getenv("ZRA_B200_ENC_PIPE") ? (u32)(atoi(getenv("ZRA_B200_ENC_PIPE")) != 0) : (lay->matchSmem >= 40u * 1024u ? 1u : 0u);
+  lay->matchSmem += (lay->matchPipe ? 2u : 1u) * (4u + 2u) * lay->matchThreads + 4u * (256u + 128u);
   lay->ctaMatch = frameSize <= 65536u && lay->matchSmem <= 226u * 1024u && !getenv("ZRA_B200_ENC_SERIAL");
   const u32 blk = frameSize < kBlockSizeMax ? frameSize : kBlockSizeMax;
   lay->seqStride = blk / 3 + 2;
@@ -815,6 +1058,8 @@ u32 launch_encode_frames(const void* dIn, u64 inOff, u64 inEnd, u32 frameSize, u
   } else {
     cudaFuncSetAttribute(k_enc_match_cta<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.matchSmem);
     cudaFuncSetAttribute(k_enc_match_cta<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.matchSmem);
+    cudaFuncSetAttribute(k_enc_match_cta_pipe<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.matchSmem);
+    cudaFuncSetAttribute(k_enc_match_cta_pipe<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.matchSmem);
   }
   const u32 tpb = 64;
   static const bool serialEntropy = getenv("ZRA_B200_ENC_SERIAL_ENTROPY") != nullptr;  // thread-per-frame stages (debugging)
@@ -823,7 +1068,10 @@ u32 launch_encode_frames(const void* dIn, u64 inOff, u64 inEnd, u32 frameSize, u
   launches++;
   for (u32 r = 0; r < lay.rounds; r++) {
     if (lay.ctaMatch) {
-      if (lay.matchThreads == 512) k_enc_match_cta<512><<<nFrames, 512, lay.matchSmem, st>>>(j, v);
+      if (lay.matchPipe) {
+        if (lay.matchThreads == 512) k_enc_match_cta_pipe<512><<<nFrames, 512, lay.matchSmem, st>>>(j, v);
+        else k_enc_match_cta_pipe<256><<<nFrames, 256, lay.matchSmem, st>>>(j, v);
+      } else if (lay.matchThreads == 512) k_enc_match_cta<512><<<nFrames, 512, lay.matchSmem, st>>>(j, v);
       else k_enc_match_cta<256><<<nFrames, 256, lay.matchSmem, st>>>(j, v);
     } else {
       k_enc_match<<<div_up(nFrames, tpb), tpb, 0, st>>>(j, v, r);

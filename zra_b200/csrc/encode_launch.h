@@ -13,6 +13,7 @@ struct EncodeLayout {
   uint32_t tabSEntries, tabLEntries;  // per frame
   uint32_t seqStride, litStride, hufStride, seqOutStride, outStride;
   uint32_t rounds;                    // blocks per frame
+  uint32_t matchPipe;                          // producer / consumer form of the matcher (experiment)
   uint32_t ctaMatch, matchSmem, matchThreads;  // frame-cooperative matcher (frames <= 64 KiB)
   uint32_t matchLogS, matchLogL, matchMls;     // its table logs (16-bit entries) and short-hash width
 };
