@@ -399,6 +399,12 @@ __global__ void __launch_bounds__(T) k_enc_match_cta_pipe(EncJob j, EncView v) {
   u32* cnt = hist + 256;
   u16* take = reinterpret_cast<u16*>(cnt + 128);  // [2][T] per position of the round: the match a walk arriving there takes
   __shared__ u32 sHas[2][T / 32];                  // per 32 positions: which of them have a match
+  // the walker leaves a round's sequence records here (one shared-memory store each); the producers, which have the
+  // slack, copy them out when they next own the buffer (a round of P positions holds at most P / 4 matches)
+  constexpr u32 kStage = T / 4;
+  __shared__ __align__(8) u64 stageRec[2][kStage];
+  __shared__ u32 stageSide[2][kStage];
+  __shared__ u32 sRoundSeq[2][2];                  // per buffer: first sequence of its round, one past the last
   const u8* base = j.in;
   const u64 fbase = j.inOff + (u64)i * j.frameSize;
   const EncScratch s = v.frame(i);
@@ -422,7 +428,11 @@ __global__ void __launch_bounds__(T) k_enc_match_cta_pipe(EncJob j, EncView v) {
     const u32 ptid = tid - 32, pwarp = warp - 1;
     for (u32 r = 0, rb = 0; r < rounds; r++, rb += P) {
       const u32 buf = r & 1u;
-      if (r >= 2) bar_sync_n(BAR_EMPTY + buf, T);  // the walker is done with this buffer (round r - 2)
+      if (r >= 2) {
+        bar_sync_n(BAR_EMPTY + buf, T);  // the walker is done with this buffer (round r - 2): its records go out
+        const u32 q0 = sRoundSeq[buf][0], q1 = sRoundSeq[buf][1];
+        for (u32 q = q0 + ptid; q < q1; q += P) { s.seqs[q] = stageRec[buf][q - q0]; side[q] = stageSide[buf][q - q0]; }
+      }
     const u32 pos = rb + ptid;
     const u32 curAnchor = sAnchorAfter[buf];  // the anchor after round r - 2 (final: EMPTY barrier above)
     const bool skip = curAnchor >= rb + P;     // the whole round lies inside a match already taken (uniform)
@@ -508,11 +518,17 @@ __global__ void __launch_bounds__(T) k_enc_match_cta_pipe(EncJob j, EncView v) {
       bar_arrive_n(BAR_FULL + buf, T);
     }
     // the walker's last arrivals (rounds whose buffers nobody reuses) are consumed here so that no barrier is left open
-    for (u32 k = rounds >= 2 ? rounds - 2 : 0; k < rounds; k++) bar_sync_n(BAR_EMPTY + (k & 1u), T);
+    for (u32 k = rounds >= 2 ? rounds - 2 : 0; k < rounds; k++) {
+      const u32 buf = k & 1u;
+      bar_sync_n(BAR_EMPTY + buf, T);
+      const u32 q0 = sRoundSeq[buf][0], q1 = sRoundSeq[buf][1];
+      for (u32 q = q0 + ptid; q < q1; q += P) { s.seqs[q] = stageRec[buf][q - q0]; side[q] = stageSide[buf][q - q0]; }
+    }
   } else {
     for (u32 r = 0, rb = 0; r < rounds; r++, rb += P) {
       const u32 buf = r & 1u;
       bar_sync_n(BAR_FULL + buf, T);
+      const u32 roundSeq0 = nseq;
       if (!sSkip[buf]) {
       {
         for (;;) {
@@ -549,8 +565,8 @@ __global__ void __launch_bounds__(T) k_enc_match_cta_pipe(EncJob j, EncView v) {
           const u32 ll = mpos - anchor;
           const u64 rec = emit_sequence(rc, ll, ml, off);
           if (lane == 0) {
-            s.seqs[nseq] = rec;
-            side[nseq] = anchor | (litPos << 16);
+            stageRec[buf][nseq - roundSeq0] = rec;
+            stageSide[buf][nseq - roundSeq0] = anchor | (litPos << 16);
           }
           nseq++;
           litPos += ll;
@@ -558,7 +574,7 @@ __global__ void __launch_bounds__(T) k_enc_match_cta_pipe(EncJob j, EncView v) {
         }
       }
       }
-      if (lane == 0) sAnchorAfter[buf] = anchor;
+      if (lane == 0) { sAnchorAfter[buf] = anchor; sRoundSeq[buf][0] = roundSeq0; sRoundSeq[buf][1] = nseq; }
       __threadfence_block();
       bar_arrive_n(BAR_EMPTY + buf, T);
     }
