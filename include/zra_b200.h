@@ -126,6 +126,13 @@ ZRA_EXPORT size_t ZraShardHeaderSize(uint64_t frames, size_t metaSize);
 ZRA_EXPORT ZraStatus ZraShardBuildHeader(uint64_t uncompressedSize, uint32_t frameSize, const void* metaBuffer, size_t metaSize,
                                          const uint64_t* frameSizes, uint64_t frames, void* out, size_t outCapacity);
 
+/* ---- integrity beyond the reference ----------------------------------------------
+ * The reference stores a CRC-32 of the header (everything but the hash field itself: fixed header, metadata, seek
+ * table; source/zra.cpp:128-133) and never checks it (zra::Header, zra.cpp:141-171). This recomputes it from the
+ * first headerSize bytes of an archive in HOST memory: Success when it matches, HeaderInvalid when the magic /
+ * version are wrong or the CRC differs, OutOfBoundsAccess when `size` is shorter than the header. Needs no GPU. */
+ZRA_EXPORT ZraStatus ZraVerifyHeaderCrc(const void* archive, size_t size);
+
 #ifdef __cplusplus
 }
 #endif

@@ -102,3 +102,26 @@ def test_gpu_entry_points_fail_loudly_without_a_device():
     assert e.value.code == zra_b200.StatusCode.ZStdError and e.value.zstd_code == 1
     with pytest.raises(zra_b200.ZraError):
         zra_b200.CudaContext(0)
+
+
+def test_header_crc_verification_needs_no_gpu():
+    """ZraVerifyHeaderCrc: the CRC-32 the reference writes (zra.cpp:128-133) and never checks. Every
+    reference-made golden archive verifies; any flipped header byte (fixed fields, metadata, seek table) is caught."""
+    import numpy as np
+    import pytest
+
+    import zra_b200
+    from common import golden_archive, golden_archives, parse_header
+
+    for name in golden_archives():
+        a, _ = golden_archive(name)
+        assert zra_b200.VerifyHeaderCrc(a), name
+        h = parse_header(a)
+        for at in (5, 19, 27, 31, 38 + h["metaSize"], h["size"] - 1, 15):
+            if at >= h["size"]:
+                continue
+            b = a.copy()
+            b[at] ^= 0x40
+            assert not zra_b200.VerifyHeaderCrc(b), (name, at)
+        with pytest.raises(zra_b200.ZraError):
+            zra_b200.VerifyHeaderCrc(a[: h["size"] - 1])

@@ -23,4 +23,5 @@ from .binding import (  # noqa: F401
     Decompressor,
     FullDecompressor,
     CudaContext,
+    VerifyHeaderCrc,
 )

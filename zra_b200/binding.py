@@ -105,6 +105,7 @@ def lib():
         "ZraCudaDecompressFrames": (ZraStatus, [vp, vp, sz, u64, u64, vp, sz, vp]),
         "ZraCudaCompressBuffer": (ZraStatus, [vp, vp, sz, vp, sz, P(sz), C.c_int8, u32, C.c_bool, vp, sz, vp]),
         "ZraCudaCompressFrames": (ZraStatus, [vp, vp, sz, u32, C.c_int8, C.c_bool, vp, sz, P(u64), P(sz), vp]),
+        "ZraVerifyHeaderCrc": (ZraStatus, [vp, sz]),
         "ZraShardHeaderSize": (sz, [u64, sz]),
         "ZraShardBuildHeader": (ZraStatus, [u64, u32, vp, sz, P(u64), u64, vp, sz]),
         "ZraCudaDecompressRABatch": (ZraStatus, [vp, vp, sz, vp, vp, vp, u32, u32, u64, vp, P(u64), P(u64), vp]),
@@ -206,6 +207,17 @@ class Header:
         if getattr(self, "_own", False) and getattr(self, "_h", None):
             lib().ZraDeleteHeader(self._h)
             self._h = None
+
+
+def VerifyHeaderCrc(archive):
+    """include/zra_b200.h: ZraVerifyHeaderCrc — recomputes the header CRC-32 the reference stores but never checks.
+    Returns True / False; raises for a truncated buffer."""
+    a = _as_array(archive)
+    st = lib().ZraVerifyHeaderCrc(_ptr(a), a.size)
+    if st.zra == StatusCode.HeaderInvalid:
+        return False
+    _check(st)
+    return True
 
 
 def _wrap_reader(fn):

@@ -200,4 +200,15 @@ ZraStatus ZraShardBuildHeader(uint64_t uncompressedSize, uint32_t frameSize, con
   return st(Success);
 }
 
+ZraStatus ZraVerifyHeaderCrc(const void* archive, size_t size) {
+  const uint8_t* p = static_cast<const uint8_t*>(archive);
+  if (!p || size < kFixedHeaderSize) return st(OutOfBoundsAccess);
+  if (get_le(p + 8, 4) != kZraMagic || get_le(p + 12, 2) > kZraVersion) return st(HeaderInvalid);
+  const uint64_t total = get_le(p + 4, 4) + 8;
+  const uint64_t expect = (uint64_t)kFixedHeaderSize + get_le(p + 34, 4) + kEntrySize * get_le(p + 26, 4);
+  if (total != expect) return st(HeaderInvalid);  // the three size fields must agree with each other
+  if (total > size) return st(OutOfBoundsAccess);
+  return st(header_hash_host(p, (size_t)total) == (uint32_t)get_le(p + 14, 4) ? Success : HeaderInvalid);
+}
+
 }  // extern "C"
