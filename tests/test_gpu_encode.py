@@ -142,3 +142,15 @@ def test_device_compress_with_metadata(tmp_path):
     assert np.array_equal(refzra.oracle_decompress_buffer(z), data)
     if refzra.have_ref():
         assert np.array_equal(refzra.ref_decompress(z), data)
+
+
+@pytest.mark.parametrize("fs,lvl", [(65536, 3), (65536, 1), (16384, 3), (262144, 3)])
+def test_compression_is_deterministic(fs, lvl):
+    """Same input, same archive, byte for byte, run after run: the shared-memory matcher inserts with a lowest-position
+    compare-and-swap and hands rounds over with barriers, so nothing may depend on thread timing (level 3 at 64 KiB is
+    the producer / consumer form of the matcher)."""
+    data = make("text", (6 << 20) + 321, fs)
+    first = zra_b200.CompressBuffer(data, lvl, fs, True)
+    for _ in range(3):
+        again = zra_b200.CompressBuffer(data, lvl, fs, True)
+        assert again.size == first.size and np.array_equal(again, first)
