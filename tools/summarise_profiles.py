@@ -45,17 +45,18 @@ if os.path.exists(lf):
             f.write(f"{n},{a[0]},{a[1]:.4f},{share:.4f},\"{a[2]}\",\"{a[3]}\"\n")
     print("wrote launches summary:", len(rows), "launches")
 
-rep = os.path.join(G, tag + "_full.ncu-rep")
-if os.path.exists(rep):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(io.StringIO(raw)))
-    hdr, units = rows[0], rows[1]
-    kn = hdr.index("Kernel Name")
-    with open(os.path.join(P, out_tag + "_ncu_full_summary.csv"), "w") as f:
-        names = [r[kn].split("(")[0] for r in rows[2:]]
-        f.write("metric,unit," + ",".join(names) + "\n")
-        for k in KEYS:
-            if k in hdr:
-                i = hdr.index(k)
-                f.write(k + "," + units[i] + "," + ",".join('"%s"' % r[i] if "," in r[i] else r[i] for r in rows[2:]) + "\n")
-    print("wrote full summary:", len(rows) - 2, "kernels")
+for suffix in ("_full", "_enc_full", "_ra_full"):
+  rep = os.path.join(G, tag + suffix + ".ncu-rep")
+  if os.path.exists(rep):
+      raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+      rows = list(csv.reader(io.StringIO(raw)))
+      hdr, units = rows[0], rows[1]
+      kn = hdr.index("Kernel Name")
+      with open(os.path.join(P, out_tag + "_ncu" + suffix + "_summary.csv"), "w") as f:
+          names = [r[kn].split("(")[0] for r in rows[2:]]
+          f.write("metric,unit," + ",".join(names) + "\n")
+          for k in KEYS:
+              if k in hdr:
+                  i = hdr.index(k)
+                  f.write(k + "," + units[i] + "," + ",".join('"%s"' % r[i] if "," in r[i] else r[i] for r in rows[2:]) + "\n")
+      print("wrote full summary:", len(rows) - 2, "kernels")
