@@ -13,8 +13,12 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-ra > gpurun_out/${tag}_ncu_bench.log 2>&1; echo "ncu launches rc=$?"
 ZRA_B200_CHUNKS=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_(block_setup|huf_decode|seq_decode|seq_execute|frame_finish)' -c 5 \
     -f -o gpurun_out/${tag}_full python tools/profile_decode.py 1024 65536 1 > gpurun_out/${tag}_ncu_full.log 2>&1; echo "ncu full rc=$?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_enc_|k_scan_|k_write_entries|k_gather_frames|k_crc_' -c 16 \
-    -f -o gpurun_out/${tag}_enc_full python tools/time_compress.py 1024 65536 3 1 mixed > gpurun_out/${tag}_ncu_enc_full.log 2>&1; echo "ncu enc full rc=$?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_ra_|k_block_setup|k_huf_decode|k_seq_decode|k_seq_execute|k_frame_finish' -c 40 \
-    -f -o gpurun_out/${tag}_ra_full python tools/profile_ra.py 1024 1 > gpurun_out/${tag}_ncu_ra_full.log 2>&1; echo "ncu ra full rc=$?"
+# encoder and random-access kernels: full-set capture, exported to raw CSV on the box (the reports are too big to bring back)
+timeout 600 ncu --set full --clock-control none -k regex:'k_enc_|k_scan_|k_write_entries|k_gather_frames|k_crc_' -c 16 \
+    -f -o /tmp/${tag}_enc_full python tools/time_compress.py 1024 65536 3 1 mixed > gpurun_out/${tag}_ncu_enc_full.log 2>&1; echo "ncu enc full rc=$?"
+ncu -i /tmp/${tag}_enc_full.ncu-rep --page raw --csv > gpurun_out/${tag}_enc_full_raw.csv 2>/dev/null
+timeout 600 ncu --set full --clock-control none -k regex:'k_ra_|k_block_setup|k_huf_decode|k_seq_decode|k_seq_execute|k_frame_finish' -c 12 \
+    -f -o /tmp/${tag}_ra_full python tools/profile_ra.py 1024 1 > gpurun_out/${tag}_ncu_ra_full.log 2>&1; echo "ncu ra full rc=$?"
+ncu -i /tmp/${tag}_ra_full.ncu-rep --page raw --csv > gpurun_out/${tag}_ra_full_raw.csv 2>/dev/null
+du -sh gpurun_out
 ls -la gpurun_out

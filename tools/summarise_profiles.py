@@ -47,13 +47,15 @@ if os.path.exists(lf):
 
 for suffix in ("_full", "_enc_full", "_ra_full"):
   rep = os.path.join(G, tag + suffix + ".ncu-rep")
-  if os.path.exists(rep):
-      raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+  rawcsv = os.path.join(G, tag + suffix + "_raw.csv")
+  if os.path.exists(rep) or os.path.exists(rawcsv):
+      raw = (subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+             if os.path.exists(rep) else open(rawcsv).read())
       rows = list(csv.reader(io.StringIO(raw)))
       hdr, units = rows[0], rows[1]
       kn = hdr.index("Kernel Name")
       with open(os.path.join(P, out_tag + "_ncu" + suffix + "_summary.csv"), "w") as f:
-          names = [r[kn].split("(")[0] for r in rows[2:]]
+          names = [r[kn].split("(")[0].replace(", ", "_").replace(",", "_") for r in rows[2:]]
           f.write("metric,unit," + ",".join(names) + "\n")
           for k in KEYS:
               if k in hdr:
