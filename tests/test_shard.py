@@ -102,3 +102,67 @@ def test_build_header_matches_the_oracle():
         o.zra_oracle_build_header(out.ctypes.data_as(C.c_void_p), n, fs, m.ctypes.data_as(C.c_void_p) if m.size else None, m.size,
                                   offs.ctypes.data_as(C.POINTER(C.c_uint64)), frames + 1)
         assert np.array_equal(got, out)
+
+
+# ---------------------------------------------------------------------------- random access over a sharded archive
+def test_route_reads_splits_at_shard_boundaries():
+    n, fs, world = 10 * 16384 + 100, 16384, 3
+    offs = np.array([0, 16384 * 3 - 10, n - 5, 16384 * 6 - 1, 50000], dtype=np.int64)
+    szs = np.array([100, 20, 5, 2 * 16384 + 2, 0], dtype=np.int64)
+    routed = shard.route_reads(offs, szs, n, fs, world)
+    seen = np.zeros(offs.size, np.int64)
+    for r, (req, inner, absolute, size) in enumerate(routed):
+        lo, hi = shard.byte_range(n, fs, r, world)
+        assert ((absolute >= lo) & (absolute + size <= hi)).all()
+        assert (absolute == offs[req] + inner).all()
+        np.add.at(seen, req, size)
+    assert (seen == szs).all()          # every byte of every read is served exactly once
+    assert len(routed[0][0]) == 2       # read 1 straddles shards 0|1 (frames 0-2 | 3-5)
+    with pytest.raises(Exception):
+        shard.route_reads(np.array([n - 4]), np.array([5]), n, fs, world)
+
+
+def _ra_worker(rank, world, port, n, fs, q):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        data = synth.text(n, seed=9, threads=1)
+        lo, hi = shard.byte_range(n, fs, rank, world)
+        mine = data[lo:hi]           # what this rank's GPU would hold decoded on demand
+
+        def serve(abs_off, sizes):
+            assert all(lo <= o and o + s <= hi for o, s in zip(abs_off, sizes))
+            return b"".join(mine[o - lo: o - lo + s].tobytes() for o, s in zip(abs_off, sizes))
+
+        rng = np.random.default_rng(100 + rank)
+        cnt = 300
+        sizes = rng.integers(0, 3 * fs, cnt).astype(np.int64)
+        offs = np.array([rng.integers(0, n - s + 1) for s in sizes], dtype=np.int64)
+        got = shard.sharded_random_access(offs, sizes, n, fs, serve)
+        want = np.concatenate([data[o: o + s] for o, s in zip(offs, sizes)]) if cnt else np.zeros(0, np.uint8)
+        q.put((rank, bool(np.array_equal(got, want)), int(got.size)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_random_access_over_gloo(world):
+    """Every rank issues its own reads into the whole archive; pieces are routed to the owners of their frames, served
+    from the owners' shards and reassembled in request order (reads crossing shard boundaries included)."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    n, fs = (1 << 20) + 4321, 16384
+    procs = [ctx.Process(target=_ra_worker, args=(r, world, port, n, fs, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(r[0] for r in res) == list(range(world))
+    assert all(r[1] for r in res), res

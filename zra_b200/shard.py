@@ -5,7 +5,9 @@ Frames are independent, so rank r of W owns the contiguous frame range frame_ran
     (ZraCudaDecompressFrames); an optional all-gather (NCCL over NVLink) assembles the output;
   * compression: every rank compresses its range (ZraCudaCompressFrames), then ONE exchange step:
     the per-frame compressed sizes are all-gathered (equivalently an exclusive scan of the per-shard
-    totals gives every shard its base offset) and the header is stitched (ZraShardBuildHeader).
+    totals gives every shard its base offset) and the header is stitched (ZraShardBuildHeader);
+  * random access: reads are routed to the owners of their frames (split at shard boundaries), served
+    from the owners' shards and returned in request order (route_reads / sharded_random_access).
 One process per GPU, torch.distributed for the plumbing (backend nccl on GPUs, gloo in the CPU tests).
 """
 import ctypes as C
@@ -79,3 +81,61 @@ def compress_shard(ctx, d_in, in_size, frame_size, level, checksum, d_out, out_c
                                  sizes.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(produced), C.c_void_p(stream))
     ctx._raise(st)
     return sizes[:frames], produced.value
+
+
+# ---------------------------------------------------------------------------- random access across shards
+def route_reads(offsets, sizes, uncompressed_size, frame_size, world):
+    """Batched random access over a sharded archive: every read goes to the rank that owns
+    `offset / frameSize`; a read that crosses a shard boundary is split into one piece per shard. Returns, per rank,
+    (request index, byte offset inside the REQUEST, absolute offset, piece size) as int64 arrays, in request order.
+    Bounds are the streaming twin's (offset + size <= uncompressedSize, source/zra.cpp:370)."""
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    sizes = np.ascontiguousarray(sizes, dtype=np.int64)
+    if offsets.size and (offsets.min() < 0 or (offsets + sizes).max() > uncompressed_size):
+        raise binding.ZraError(binding.StatusCode.OutOfBoundsAccess)
+    bounds = np.array([byte_range(uncompressed_size, frame_size, r, world)[0] for r in range(world)] + [uncompressed_size], dtype=np.int64)
+    out = []
+    for r in range(world):
+        lo, hi = bounds[r], bounds[r + 1]
+        a = np.maximum(offsets, lo)
+        b = np.minimum(offsets + sizes, hi)
+        hit = np.nonzero(b > a)[0]
+        out.append((hit.astype(np.int64), (a[hit] - offsets[hit]).astype(np.int64), a[hit].astype(np.int64), (b[hit] - a[hit]).astype(np.int64)))
+    return out
+
+
+def sharded_random_access(offsets, sizes, uncompressed_size, frame_size, serve, group=None):
+    """Every rank calls this with ITS OWN batch of reads into the whole (sharded) archive and a `serve(abs_offsets,
+    sizes) -> bytes` that answers reads inside its shard (on a GPU box: ZraCudaDecompressRABatch on the resident shard).
+    Two exchange steps (all-to-all of the routed pieces, all-to-all of their bytes) and the results come back in the
+    caller's request order as one uint8 array (reads back to back). Backend-agnostic: object collectives keep the CPU
+    tests simple; a production caller would exchange the same arrays with all_to_all_single over NCCL."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    routed = route_reads(offsets, sizes, uncompressed_size, frame_size, world)
+    # step 1: pieces to their owners (every rank publishes its W outgoing lists; rank r takes the r-th of each)
+    me = dist.get_rank(group)
+    everyone = [None] * world
+    dist.all_gather_object(everyone, [(p[2], p[3]) for p in routed], group=group)
+    inbox = [everyone[src][me] for src in range(world)]
+    # serve every sender's pieces from the local shard
+    answers = []
+    for abs_off, sz in inbox:
+        answers.append(bytes(serve(abs_off, sz)) if len(sz) else b"")
+    # step 2: bytes back to the requesters
+    everyone = [None] * world
+    dist.all_gather_object(everyone, answers, group=group)
+    sizes = np.ascontiguousarray(sizes, dtype=np.int64)
+    starts = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int64) if sizes.size else np.zeros(0, np.int64)
+    out = np.empty(int(sizes.sum()), np.uint8)
+    for owner in range(world):
+        req, inner, _, psz = routed[owner]
+        blob = np.frombuffer(everyone[owner][me], dtype=np.uint8)
+        cur = 0
+        for k in range(req.size):
+            n = int(psz[k])
+            at = int(starts[req[k]] + inner[k])
+            out[at: at + n] = blob[cur: cur + n]
+            cur += n
+    return out
