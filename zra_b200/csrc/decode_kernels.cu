@@ -706,8 +706,19 @@ __global__ void k_frame_finish(const u8* __restrict__ src, const u8* __restrict_
     p = dst + descs[i].dstOff;
     u32 stripes = len >> 5;
     if (((uintptr_t)p & 7) == 0) {
+      // 16 independent loads in flight before the dependent rounds: with few, large frames (256 KiB: 8192 rounds per
+      // lane) this loop is load-latency bound, not bandwidth bound
       const u64* w = reinterpret_cast<const u64*>(p) + q;
-      for (u32 k = 0; k < stripes; k++) acc = xxh_round(acc, w[4 * (u64)k]);
+      u32 k = 0;
+      for (; k + 16 <= stripes; k += 16) {
+        u64 v[16];
+#pragma unroll
+        for (u32 j = 0; j < 16; j++)  // volatile asm: the compiler otherwise sinks most of the loads between the rounds
+          asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(v[j]) : "l"(w + 4 * (u64)(k + j)));
+#pragma unroll
+        for (u32 j = 0; j < 16; j++) acc = xxh_round(acc, v[j]);
+      }
+      for (; k < stripes; k++) acc = xxh_round(acc, w[4 * (u64)k]);
     } else {
       const u8* b = p + 8 * q;
       for (u32 k = 0; k < stripes; k++) acc = xxh_round(acc, ld64(b + 32 * (u64)k));
