@@ -62,6 +62,7 @@ namespace zra {
   };
 
   // Thrown by every function below on failure.
+  // reference: include/zra.hpp:70-88, source/zra.cpp:48-82
   struct ZRA_EXPORT Exception : std::exception {
     StatusCode code;  // what failed
     int zstdCode;     // ZSTD_ErrorCode when code == ZStdError
@@ -72,9 +73,11 @@ namespace zra {
   };
 
   // Highest archive format version supported (1).
+  // reference: include/zra.hpp:91, source/zra.cpp:84-87
   ZRA_EXPORT u16 GetVersion();
 
   // Parsed archive header. Keeps the read callback to fetch metadata / seek table on demand.
+  // reference: include/zra.hpp:96-131, source/zra.cpp:141-187
   class ZRA_EXPORT Header {
    private:
     std::function<void(size_t, size_t, void*)> readFunction;
@@ -100,20 +103,25 @@ namespace zra {
   };
 
   // Worst-case archive size for inputSize bytes in frameSize frames with metaSize metadata bytes.
+  // reference: include/zra.hpp:139, source/zra.cpp:189-192
   ZRA_EXPORT size_t GetOutputBufferSize(size_t inputSize, u32 frameSize, u32 metaSize = 0);
 
   // Whole-buffer compression into `output` (capacity >= GetOutputBufferSize); returns the archive size.
+  // reference: include/zra.hpp:151, source/zra.cpp:194-234
   ZRA_EXPORT size_t CompressBuffer(const BufferView& input, const BufferView& output, i8 compressionLevel = 0,
                                    u32 frameSize = 16384, bool checksum = true, const BufferView& meta = {});
   // Same, returning a right-sized Buffer.
+  // reference: include/zra.hpp:162, source/zra.cpp:236-241
   ZRA_EXPORT Buffer CompressBuffer(const BufferView& buffer, i8 compressionLevel = 0, u32 frameSize = 16384,
                                    bool checksum = true, const BufferView& meta = {});
 
   // Whole-archive decompression; `output` must hold Header::uncompressedSize bytes.
+  // reference: include/zra.hpp:169,176, source/zra.cpp:243-256
   ZRA_EXPORT void DecompressBuffer(const BufferView& input, const BufferView& output);
   ZRA_EXPORT Buffer DecompressBuffer(const BufferView& buffer);
 
   // Random access: `size` bytes of the original data starting at `offset`.
+  // reference: include/zra.hpp:185,194, source/zra.cpp:258-302
   ZRA_EXPORT void DecompressRA(const BufferView& input, const BufferView& output, size_t offset, size_t size);
   ZRA_EXPORT Buffer DecompressRA(const BufferView& buffer, size_t offset, size_t size);
 
@@ -121,6 +129,7 @@ namespace zra {
   struct Entry;  // 5-byte seek-table slot (opaque)
 
   // Streaming compression: feed the input in frame-aligned chunks, write the header last.
+  // reference: include/zra.hpp:202-254, source/zra.cpp:304-365
   class ZRA_EXPORT Compressor {
    private:
     std::shared_ptr<ZCCtx> ctx;
@@ -149,6 +158,7 @@ namespace zra {
   class ZDCtx;  // GPU decompression context (opaque)
 
   // Streaming random access over a read callback.
+  // reference: include/zra.hpp:261-299, source/zra.cpp:367-424
   class ZRA_EXPORT Decompressor {
    private:
     std::shared_ptr<ZDCtx> ctx;
@@ -172,6 +182,7 @@ namespace zra {
   };
 
   // Streaming front-to-back decompression over a read callback.
+  // reference: include/zra.hpp:303-324, source/zra.cpp:426-436
   class ZRA_EXPORT FullDecompressor {
    private:
     std::shared_ptr<ZDCtx> ctx;
