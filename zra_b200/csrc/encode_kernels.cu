@@ -1011,7 +1011,11 @@ size_t encode_scratch_bytes(u32 nFrames, u32 frameSize, u32 lastFrameLen, int le
     // +0.81 % (text); mixed +0.20 %. The 3 % ratio bound of north_star holds with margin.
     u32 dS = ls, dL = ll;
     if (ll) { dS = ls > 12 ? ls - 2 : (ls > 10 ? 10 : ls); dL = ll > 12 ? ll - 2 : (ll > 10 ? 10 : ll); }
-    else if (ls > 13) dS = ls - 1;  // fast levels, big tables: level 2 / 64 KiB 15 -> 14: 10.7 -> 17.9 GB/s, archive -0.36 % -> +0.67 %
+    // fast levels: 2^14 entries whatever the reference's log (13..15). Level 2 / 64 KiB 15 -> 14: 10.7 -> 17.9 GB/s,
+    // archive -0.36 % -> +0.67 %; level 1 / 64 KiB 13 -> 14: the reference's repeat-offset probes find 4-5 byte matches
+    // this matcher (minimum match 6 there) does not, which cost +2.9 % on text at log 13 — too close to the 3 % bound;
+    // at log 14: +0.8 % for 10 % of the speed (profiles/r02l_ratio.jsonl and the run after it)
+    else if (ls >= 13) dS = 14;
     lay->matchLogS = envu("ZRA_B200_ENC_LOGS", dS);
     lay->matchLogL = envu("ZRA_B200_ENC_LOGL", dL);
     lay->matchMls = envu("ZRA_B200_ENC_MLS", frameSize <= (16u << 10) ? (lv <= 1 ? 5u : 4u) : mlsTab[lv < 0 ? 0 : (lv > 4 ? 4 : lv)]);
