@@ -22,6 +22,15 @@ def make(kind, n, fs, seed=1):
         return synth.random_bytes(n, seed=seed, threads=4)
     if kind == "zeros":
         return np.zeros(n, np.uint8)
+    if kind.startswith("datagen"):  # zstd's own synthetic generator (programs/datagen.c), compressibility -P<nn>
+        import os
+        import subprocess
+
+        gen = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "datagen")
+        if not os.path.exists(gen):
+            pytest.skip("oracle/_ref/datagen not present")
+        raw = subprocess.run([gen, f"-g{n}", f"-P{kind[7:]}", f"-s{seed}"], capture_output=True, check=True).stdout
+        return np.frombuffer(raw, dtype=np.uint8)[:n].copy()
     raise ValueError(kind)
 
 
@@ -73,7 +82,8 @@ def test_compress_buffer_roundtrip(kind, n, fs, lvl, ck):
 
 @needs_ref
 @pytest.mark.parametrize("kind,fs,lvl", [("text", 16384, 3), ("text", 65536, 1), ("text", 65536, 2), ("text", 65536, 3),
-                                         ("text", 262144, 3), ("mixed", 65536, 1), ("mixed", 65536, 3), ("text", 16384, 1)])
+                                         ("text", 262144, 3), ("mixed", 65536, 1), ("mixed", 65536, 3), ("text", 16384, 1),
+                                         ("datagen50", 65536, 1), ("datagen80", 65536, 3), ("datagen20", 16384, 2), ("datagen80", 65536, 1)])
 def test_ratio_within_3_percent_of_reference(kind, fs, lvl):
     n = 16 << 20
     data = make(kind, n, fs, seed=fs + lvl)
@@ -83,6 +93,8 @@ def test_ratio_within_3_percent_of_reference(kind, fs, lvl):
     delta = ours.size / ref.size - 1
     # never more than 3 % larger than the reference; the parallel matcher inserts every position, so it may be smaller
     assert -0.10 < delta < 0.03, (ours.size, ref.size, delta)
+    if fs <= 65536:  # the shared-memory matcher: measured within +1.1 % everywhere (profiles/r02m_ratio.jsonl); keep a margin
+        assert delta < 0.02, (ours.size, ref.size, delta)
     # the headers have the same length and, apart from hash and table values, the same bytes
     ho, hr = parse_header(ours), parse_header(ref)
     for k in ("frameId", "headerSize", "magic", "version", "uncompressedSize", "tableSize", "frameSize", "metaSize"):
