@@ -141,11 +141,22 @@ def test_corruption_is_detected():
 
 @needs_ref
 @pytest.mark.parametrize("kind,fs,lvl,ck", [("text", 16384, 3, True), ("text", 65536, 1, False), ("text", 262144, 3, True),
-                                            ("mixed", 65536, 2, True), ("text", 5000, 7, True), ("random", 16384, 3, True)])
+                                            ("mixed", 65536, 2, True), ("text", 5000, 7, True), ("random", 16384, 3, True),
+                                            ("datagen30", 16384, 3, True), ("datagen70", 262144, 1, True), ("datagen95", 65536, 9, True)])
 def test_fresh_reference_archives(kind, fs, lvl, ck):
     n = 1_000_003
-    data = {"text": synth.text, "random": synth.random_bytes}.get(kind, None)
-    data = synth.mixed(n, period=fs, threads=1) if kind == "mixed" else data(n, seed=fs + lvl, threads=1)
+    if kind.startswith("datagen"):  # zstd's own generator (programs/datagen.c): other match / literal statistics than the text model
+        import os
+        import subprocess
+
+        gen = os.path.join(os.path.dirname(refzra.REF_SO), "datagen")
+        if not os.path.exists(gen):
+            pytest.skip("oracle/_ref/datagen not present")
+        data = np.frombuffer(subprocess.run([gen, f"-g{n}", f"-P{kind[7:]}", "-s3"], capture_output=True, check=True).stdout,
+                             dtype=np.uint8)[:n].copy()
+    else:
+        data = {"text": synth.text, "random": synth.random_bytes}.get(kind, None)
+        data = synth.mixed(n, period=fs, threads=1) if kind == "mixed" else data(n, seed=fs + lvl, threads=1)
     z = refzra.ref_compress(data, lvl, fs, ck)
     assert np.array_equal(refzra.oracle_decompress_buffer(z), data)
     assert np.array_equal(refzra.ref_decompress(z), data)
