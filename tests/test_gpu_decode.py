@@ -276,11 +276,24 @@ def test_corruption_matches_oracle():
     ("mixed", 1 << 20, 3, False, 12 << 20),
     ("text", 3000, 9, True, 3 << 20),
     ("zeros", 65536, 3, True, 16 << 20),
+    ("datagen40", 65536, 3, True, 24 << 20),    # zstd's own generator: other match / literal statistics than the text model
+    ("datagen90", 16384, 5, True, 8 << 20),
+    ("datagen10", 262144, 1, True, 16 << 20),
 ])
 def test_reference_archives_roundtrip(torch_cuda, ctx, kind, fs, lvl, ck, n):
     """encode (reference, host cores) -> decode (CUDA): size-independent round-trip property."""
     torch = torch_cuda
-    data = (synth.mixed(n, period=fs) if kind == "mixed" else np.zeros(n, np.uint8) if kind == "zeros" else synth.text(n, seed=fs + lvl))
+    if kind.startswith("datagen"):
+        import os
+        import subprocess
+
+        gen = os.path.join(os.path.dirname(refzra.REF_SO), "datagen")
+        if not os.path.exists(gen):
+            pytest.skip("oracle/_ref/datagen not present")
+        data = np.frombuffer(subprocess.run([gen, f"-g{n}", f"-P{kind[7:]}", "-s5"], capture_output=True, check=True).stdout,
+                             dtype=np.uint8)[:n].copy()
+    else:
+        data = (synth.mixed(n, period=fs) if kind == "mixed" else np.zeros(n, np.uint8) if kind == "zeros" else synth.text(n, seed=fs + lvl))
     z = refzra.ref_compress_mt(data, lvl, fs, ck)
     got = zra_b200.DecompressBuffer(z)
     assert np.array_equal(got, data)
