@@ -511,6 +511,16 @@ ZRA_DEV u32 seq_begin(const u8* srcBase, const FrameDesc& d, const FrameCtx& c, 
   return ZE_OK;
 }
 
+ZRA_DEV u32 sel32(bool c, u32 a, u32 b) {
+#if defined(__CUDA_ARCH__)
+  u32 r;
+  asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\tselp.b32 %0, %1, %2, p;\n\t}" : "=r"(r) : "r"(a), "r"(b), "r"((u32)c));
+  return r;
+#else
+  return c ? a : b;
+#endif
+}
+
 // Decodes and validates ONE sequence, completely branch-free in the common case (lanes of a warp
 // run this in lock-step on unrelated frames, so every data-dependent branch would serialise).
 // tLL/tML/tOF are the compact tables (shared memory in the kernel), lutLL/lutML the packed
@@ -556,7 +566,9 @@ ZRA_DEV u64 seq_step(const CSym* tLL, const CSym* tML, const CSym* tOF, const u3
   const bool isRep = ofc <= 1;
   const u32 idx = ofc + ofx + ll0;                      // only meaningful when isRep: 0..3
   const u32 newOff = (1u << (ofc & 31u)) - 3u + ofx;    // only meaningful when !isRep
-  u32 repv = idx == 0 ? s.rep0 : (idx == 1 ? s.rep1 : (idx == 2 ? s.rep2 : s.rep0 - 1u));
+  // select chain, not branches: the lanes of a warp are unrelated frames, a taken branch here serialises them
+  // (profiles/r02i_source_k_seq_decode.txt: 6.7 % of the instructions, 11.4 % of the stall samples on this line)
+  u32 repv = sel32(idx == 0, s.rep0, sel32(idx == 1, s.rep1, sel32(idx == 2, s.rep2, s.rep0 - 1u)));
   repv += !repv;
   const u32 offset = isRep ? repv : newOff;
   if (!isRep || idx >= 2) s.rep2 = s.rep1;
