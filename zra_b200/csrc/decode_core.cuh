@@ -192,6 +192,10 @@ ZRA_DEV SetupCursor block_setup_head(const u8* srcBase, const FrameDesc& d, Fram
       else if (fmt == 2) { lh = 4; litSize = (w >> 4) & 0x3FFF; cs = w >> 18; }
       else { lh = 5; litSize = (w >> 4) & 0x3FFFF; cs = (w >> 22) + ((u32)b[4] << 10); }
       if (litSize > kBlockSizeMax || cs + lh > csz) { frame_fail(c, ZE_CORRUPTION); return cur; }
+      // every literal ends up in the output: a literals section larger than what is left of the frame cannot decode
+      // (zstd fails it with dstSize_tooSmall once the bytes are copied out, zstd_decompress_block.c:1049-1051), and
+      // the per-frame literal scratch is sized by the frame, so it must be refused BEFORE the Huffman stage runs
+      if (litSize > d.dstCap - c.dstPos) { frame_fail(c, ZE_DST_TOO_SMALL); return cur; }
       u32 hoff = content + lh, hlen = cs;
       if (ltype == 2) {
         u8 weights[256];
@@ -506,7 +510,9 @@ ZRA_DEV u32 seq_begin(const u8* srcBase, const FrameDesc& d, const FrameCtx& c, 
   s.br.p -= (i32)(s.llLog + s.ofLog + s.mlLog);
   s.rep0 = c.rep[0]; s.rep1 = c.rep[1]; s.rep2 = c.rep[2];
   s.litUsed = 0; s.produced = 0; s.i = 0; s.n = c.nbSeq;
-  s.litSize = c.litSize; s.room = d.dstCap - c.blkDst; s.blkDst = c.blkDst;
+  s.litSize = c.litSize; s.blkDst = c.blkDst;
+  // a block regenerates at most Block_Maximum_Size bytes (format doc :329-417); the cumulative record fields rely on it
+  s.room = d.dstCap - c.blkDst < kBlockSizeMax ? d.dstCap - c.blkDst : kBlockSizeMax;
   s.err = 0;
   return ZE_OK;
 }

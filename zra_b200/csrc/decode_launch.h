@@ -33,7 +33,7 @@ class KernelTimer {
 
 // Byte offsets of the per-batch device scratch regions, all 256-byte aligned.
 struct DecodeLayout {
-  size_t offDescs, offCtxs, offTabs, offLit, offSeqs, offSummary, offWork, offHufList, offSeqList;
+  size_t offDescs, offCtxs, offTabs, offLit, offSeqs, offSummary, offWork, offHufList, offSeqList, offRedoList;
   uint32_t litStride;  // bytes of literal scratch per frame
   uint32_t seqStride;  // packed sequence records per frame
 };
@@ -50,8 +50,9 @@ void launch_build_descs(const void* archive, uint64_t tableOff, uint64_t headerS
                         uint64_t uncompressedSize, uint32_t frameSize, uint32_t firstFrame, uint32_t nFrames, uint64_t dstBase,
                         void* scratch, const DecodeLayout& lay, cudaStream_t st, KernelTimer* timer = nullptr);
 
-// Runs `rounds` rounds (one block of every frame per round). `first` resets the frame contexts.
-void launch_decode_rounds(const void* src, void* dst, uint32_t nFrames, uint32_t rounds, bool first, void* scratch,
+// Runs `rounds` rounds (one block of every frame per round). `first` resets the frame contexts. Returns the number of
+// kernels launched.
+uint32_t launch_decode_rounds(const void* src, void* dst, uint32_t nFrames, uint32_t rounds, bool first, void* scratch,
                           const DecodeLayout& lay, cudaStream_t st, KernelTimer* timer = nullptr);
 
 // Checksums + final checks + summary. May be called again after extra rounds.

@@ -287,8 +287,7 @@ DecodeResult GpuContext::decode(const void* dSrc, size_t srcSize, const HostFram
                            (uint32_t)(firstFrame + c.f0), c.n, firstFrame * info->frameSize, c.scratch, c.lay, c.st, tm);
         launches_ += 1;
       }
-      launch_decode_rounds(dSrc, dDst, c.n, baseRounds, true, c.scratch, c.lay, c.st, tm);
-      launches_ += 4ull * baseRounds;
+      launches_ += launch_decode_rounds(dSrc, dDst, c.n, baseRounds, true, c.scratch, c.lay, c.st, tm);
       if (!enqueue_tail(c)) return fail_cuda();
     }
     for (Chunk& c : chunks)
@@ -306,8 +305,7 @@ DecodeResult GpuContext::decode(const void* dSrc, size_t srcSize, const HostFram
       for (int pass = 0; c.summary[0] == 0xFFFFFFFFu && c.summary[1] != 0 && pass < (1 << 16); pass++) {
         // frames with more blocks than the zstd encoder would emit: keep going (rare, serial)
         rounds = std::min<uint32_t>(rounds * 2, 64);
-        launch_decode_rounds(dSrc, dDst, c.n, rounds, false, c.scratch, c.lay, c.st, tm);
-        launches_ += 4ull * rounds;
+        launches_ += launch_decode_rounds(dSrc, dDst, c.n, rounds, false, c.scratch, c.lay, c.st, tm);
         if (!enqueue_tail(c) || check(cudaStreamSynchronize(c.st), "decode kernels")) return fail_cuda();
         if (tm) tm->collect();
         extra = true;

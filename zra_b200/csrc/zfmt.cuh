@@ -21,6 +21,13 @@
 #define ZRA_CONST_TABLE static const
 #endif
 
+// Dynamic shared memory of a kernel (the host logic build takes it from the SIMT emulator, tests/host_sim/simt.h).
+#if defined(__CUDACC__)
+#define ZRA_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#else
+#define ZRA_DYN_SMEM(name) unsigned char* name = simt::dyn_smem()
+#endif
+
 namespace zrab {
 
 typedef uint8_t u8;
