@@ -39,6 +39,8 @@ struct Block {
   unsigned cur{0}, nThreads{0};
   // __syncthreads
   unsigned barArrived{0}, barGen{0};
+  // named barriers (bar.sync / bar.arrive id, count)
+  unsigned nbArrived[16] = {}, nbGen[16] = {};
   unsigned long progress{0};
   std::vector<unsigned char> dynSmem;
   const std::function<void()>* body{nullptr};
@@ -86,6 +88,7 @@ inline void launch(Dim3 grid, Dim3 block, size_t dynSmemBytes, const std::functi
         blk.dynSmem.assign(dynSmemBytes + 64, 0xCD);
         blk.barArrived = 0;
         blk.barGen = 0;
+        for (int q = 0; q < 16; q++) { blk.nbArrived[q] = 0; blk.nbGen[q] = 0; }
         for (unsigned t = 0; t < n; t++) {
           blk.done[t] = 0;
           blk.warps[t >> 5].alive |= 1u << (t & 31);
@@ -163,6 +166,15 @@ inline void syncthreads() {
       if (b->barArrived >= n2) { b->barArrived = 0; b->barGen++; b->progress++; }
     }
   }
+}
+
+// bar.sync id, count (wait = true) / bar.arrive id, count (wait = false)
+inline void named_barrier(unsigned id, unsigned count, bool wait) {
+  Block* b = cur_block();
+  const unsigned gen = b->nbGen[id];
+  b->progress++;
+  if (++b->nbArrived[id] >= count) { b->nbArrived[id] = 0; b->nbGen[id]++; return; }
+  if (wait) while (b->nbGen[id] == gen) yield();
 }
 
 inline unsigned char* dyn_smem() {

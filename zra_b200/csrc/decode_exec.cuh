@@ -27,8 +27,8 @@ namespace zrab {
 
 constexpr u32 kExecFull = 0xFFFFFFFFu;
 constexpr u32 kLongCopy = 32;    // direct path: copies at least this long are done by the whole warp
-constexpr u32 kExecWarps = 8;
-constexpr u32 kTileBytes = 1024;
+constexpr u32 kExecWarps = 4;
+constexpr u32 kTileBytes = 512;
 constexpr u32 kShortMax = 64;    // groups whose literal runs and matches are all shorter go through the tile
 constexpr u32 kRunLit = 0x40000000u;  // `off` field of a literal run: tile offset - off is far below the tile
 constexpr u32 kMark = 0xFFFFu;
@@ -160,9 +160,9 @@ ZRA_DEV void exec_block(const u8* src, u8* dst, const FrameDesc& d, const FrameC
   u64 sNext = nbSeq ? ld_rec(sq + (lane < nbSeq ? lane : nbSeq - 1)) : 0ull;
   for (u32 base = 0; base < nbSeq; base += 32) {
     const u64 s = sNext;
-    {
+    if (base + 32 < nbSeq) {
       const u32 nidx = base + 32 + lane;
-      if (base + 32 < nbSeq) sNext = ld_rec(sq + (nidx < nbSeq ? nidx : nbSeq - 1));
+      sNext = ld_rec(sq + (nidx < nbSeq ? nidx : nbSeq - 1));
     }
     u64 p = shfl64_up1(s);
     if (lane == 0) p = carry;

@@ -50,10 +50,17 @@ void launch_build_descs(const void* archive, uint64_t tableOff, uint64_t headerS
                         uint64_t uncompressedSize, uint32_t frameSize, uint32_t firstFrame, uint32_t nFrames, uint64_t dstBase,
                         void* scratch, const DecodeLayout& lay, cudaStream_t st, KernelTimer* timer = nullptr);
 
+// A second stream (and two events) on which a round's Huffman stage runs BESIDE its sequence stage: both depend only on
+// the block setup, both are latency-bound, and the execute kernel needs both.
+struct SideLane {
+  cudaStream_t st{nullptr};
+  cudaEvent_t fork{nullptr}, join{nullptr};
+};
+
 // Runs `rounds` rounds (one block of every frame per round). `first` resets the frame contexts. Returns the number of
 // kernels launched.
 uint32_t launch_decode_rounds(const void* src, void* dst, uint32_t nFrames, uint32_t rounds, bool first, void* scratch,
-                          const DecodeLayout& lay, cudaStream_t st, KernelTimer* timer = nullptr);
+                          const DecodeLayout& lay, cudaStream_t st, KernelTimer* timer = nullptr, const SideLane* side = nullptr);
 
 // Checksums + final checks + summary. May be called again after extra rounds.
 void launch_frame_finish(const void* src, const void* dst, uint32_t nFrames, void* scratch, const DecodeLayout& lay,

@@ -98,7 +98,7 @@ struct FastSeq {
 };
 
 // Requests (cp.async: LDGSTS, no register staging) the 4-word group below reqW if `on` and the cursor word k is within
-// `lead` words of it, as its own commit group. Never goes below word 0: bits under the stream's first group read as
+// `lead` words of it (the caller commits). Never goes below word 0: bits under the stream's first group read as
 // whatever the ring holds (an over-read is caught by p != b0 at the end). Word w lives in ring row w & 31; rows 29..31
 // are written twice (mirror rows -3..-1), so that the four words below any cursor sit at fixed offsets from one address.
 ZRA_DEV void ring_request(FastSeq& s, const SeqSm& sm, i32 k, i32 lead, bool on) {
@@ -113,8 +113,7 @@ ZRA_DEV void ring_request(FastSeq& s, const SeqSm& sm, i32 k, i32 lead, bool on)
       "@p cp.async.ca.shared.global [%0], [%1], 4;\n\t@p cp.async.ca.shared.global [%0+128], [%1+4], 4;\n\t"
       "@p cp.async.ca.shared.global [%0+256], [%1+8], 4;\n\t@p cp.async.ca.shared.global [%0+384], [%1+12], 4;\n\t"
       "@q cp.async.ca.shared.global [%0+-3968], [%1+4], 4;\n\t@q cp.async.ca.shared.global [%0+-3840], [%1+8], 4;\n\t"
-      "@q cp.async.ca.shared.global [%0+-3712], [%1+12], 4;\n\t"
-      "@p cp.async.commit_group;\n\t}"
+      "@q cp.async.ca.shared.global [%0+-3712], [%1+12], 4;\n\t}"
       ::"r"(dst), "l"(src), "r"((u32)go), "r"(row) : "memory");
 #else
   if (go) {
@@ -125,6 +124,33 @@ ZRA_DEV void ring_request(FastSeq& s, const SeqSm& sm, i32 k, i32 lead, bool on)
   }
 #endif
   s.reqW = go ? w : s.reqW;
+}
+
+ZRA_DEV void cp_async_commit() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+
+// Refill point of the lock-step loops: at most two steps (< 6 words) are consumed between two points.
+// cp.async groups are tracked per WARP, and with 32 unrelated streams some lane asks for a group at almost every point:
+// waiting for "all but the newest group" would expose the memory latency of the previous point's request at every
+// point (profiles/r03e: 19 % of the kernel's stall samples). So a lane keeps its requests 24..28 words below its
+// cursor — one group per point — and the warp waits for all but the newest THREE groups: what a lane requested three or
+// more points ago has landed, i.e. everything above reqW + 12 <= cursor - 6. A stream of maximal sequences (> 4 words a
+// point) could outrun one request per point; then (any lane closer than 18 words) every lane may request a second
+// group and the warp waits for everything.
+ZRA_DEV void refill_point(FastSeq& s, const SeqSm& sm, bool active) {
+  const i32 kw = (s.p - 1) >> 5;
+  ring_request(s, sm, kw, 24, active);
+  if (__any_sync(kSeqFull, active && s.reqW > 0 && kw - s.reqW < 18)) {
+    ring_request(s, sm, kw, 24, active);
+    cp_async_commit();
+    cp_async_wait<0>();
+  } else {
+    cp_async_commit();
+    cp_async_wait<3>();
+  }
 }
 
 // The 96-bit window at the cursor: bit 31 of H is the next unread bit.
@@ -149,13 +175,14 @@ ZRA_DEV bool fast_begin(const u8* srcBase, const FrameDesc& d, const FrameCtx& c
   s.g0 = reinterpret_cast<const u32*>(grp);
   s.b0 = (i32)(first - grp) * 8;
   s.p = s.b0 + (i32)((len - 1) * 8 + highbit32(last));
-  // initial fill: the top six groups (24 words), synchronously
+  // initial fill: the top seven groups (28 words), synchronously
   const i32 k = (s.p - 1 >= 0 ? s.p - 1 : 0) >> 5;
   s.reqW = (k & ~3) + 4;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-  for (u32 g = 0; g < 6; g++) ring_request(s, sm, k, 1 << 30, true);
+  for (u32 g = 0; g < 7; g++) ring_request(s, sm, k, 1 << 30, true);
+  cp_async_commit();
   cp_async_wait<0>();
   s.llLog = c.llLog; s.ofLog = c.ofLog; s.mlLog = c.mlLog;
   // initial states: LL, OF, ML in that order (zstd_decompress_block.c:1000-1003)
@@ -271,7 +298,10 @@ __global__ void __launch_bounds__(32) k_seq_decode(const u8* __restrict__ src, c
   bool active = false, exhausted = false;
   u32 frame = kSeqNone;
   FastSeq st;
-  st.i = 0; st.n = 0; st.p = 0; st.reqW = 0; st.g0 = nullptr;
+  st.i = 0; st.n = 0; st.p = 0; st.b0 = 0; st.reqW = 0; st.g0 = nullptr;
+  st.aLL = sm.tLL; st.aML = sm.tML; st.aOF = sm.tOF;  // a lane without a frame steps too: its cells must be addresses
+  st.llLog = st.mlLog = st.ofLog = 0;
+  st.rep0 = st.rep1 = st.rep2 = 1; st.litUsed = st.produced = st.litSize = st.room = st.blkDst = st.bad = 0;
   u64* out = nullptr;
   for (;;) {
     // ---- idle lanes pull frames; the warp stages their tables
@@ -314,24 +344,22 @@ __global__ void __launch_bounds__(32) k_seq_decode(const u8* __restrict__ src, c
 #pragma unroll 1
 #endif
     for (u32 k = 0; k < steps; k += 2) {
-      // refill point: at most two steps (< 6 words) between points. One group per point keeps the requests 16..20 words
-      // below the cursor and a group is needed ~10 points after its request; a stream of maximal sequences could
-      // outrun one group per point, hence the (never taken) second request. Every request is its own commit group:
-      // waiting for all but the newest costs nothing unless the stream really is that dense.
-      const i32 kw = (st.p - 1) >> 5;
-      ring_request(st, sm, kw, 20, active);
-      if (__any_sync(kSeqFull, active && st.reqW > 0 && kw - st.reqW < 12)) ring_request(st, sm, kw, 12, active);
-      cp_async_wait<1>();
-      if (active) {
-        out[0] = fast_step<false>(sm, st);
-        if (k + 1 < steps) out[1] = fast_step<false>(sm, st);
-        out += 2;
+      refill_point(st, sm, active);
+      // every lane steps (a lane without a frame walks harmlessly through its own slot and ring): no branch, only the
+      // record store is predicated
+      const u64 r0 = fast_step<false>(sm, st);
+      if (active) out[0] = r0;
+      if (k + 1 < steps) {
+        const u64 r1 = fast_step<false>(sm, st);
+        if (active) out[1] = r1;
       }
+      out += 2;
     }
     if (active && (steps & 1u)) out -= 1;
     // ---- lanes at their last sequence: no state update, then the end-of-block checks
     if (active && st.n - st.i == 1u) {
-      ring_request(st, sm, (st.p - 1) >> 5, 20, true);
+      ring_request(st, sm, (st.p - 1) >> 5, 24, true);
+      cp_async_commit();
       cp_async_wait<0>();
       *out = fast_step<true>(sm, st);
       const u32 lastLits = st.litSize - st.litUsed;

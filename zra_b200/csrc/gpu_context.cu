@@ -33,6 +33,9 @@ GpuContext::GpuContext(int device) {
     for (int i = 0; i < kPoolStreams; i++) {
       int prio = flat ? least : std::min(least, greatest + i);
       if (check(cudaStreamCreateWithPriority(&pool_[i], cudaStreamNonBlocking, prio), "cudaStreamCreate")) return;
+      if (check(cudaStreamCreateWithPriority(&side_[i].st, cudaStreamNonBlocking, prio), "cudaStreamCreate")) return;
+      if (check(cudaEventCreateWithFlags(&side_[i].fork, cudaEventDisableTiming), "cudaEventCreate")) return;
+      if (check(cudaEventCreateWithFlags(&side_[i].join, cudaEventDisableTiming), "cudaEventCreate")) return;
     }
   }
   if (check(cudaEventCreateWithFlags(&forkEvent_, cudaEventDisableTiming), "cudaEventCreate")) return;
@@ -54,6 +57,11 @@ GpuContext::~GpuContext() {
     if (b->p) cudaFree(b->p);
   for (auto& s : pool_)
     if (s) cudaStreamDestroy(s);
+  for (auto& l : side_) {
+    if (l.st) cudaStreamDestroy(l.st);
+    if (l.fork) cudaEventDestroy(l.fork);
+    if (l.join) cudaEventDestroy(l.join);
+  }
   if (forkEvent_) cudaEventDestroy(forkEvent_);
   for (cudaEvent_t e : upEvents_) cudaEventDestroy(e);
   for (cudaEvent_t e : doneEvents_) cudaEventDestroy(e);
@@ -136,7 +144,8 @@ static size_t scratch_budget() {
 static uint32_t chunk_target() {
   static uint32_t v = [] {
     const char* s = getenv("ZRA_B200_CHUNKS");
-    uint32_t n = s ? (uint32_t)strtoul(s, nullptr, 10) : 4;
+    // device-resident calls: 2 chunks (1 GiB of 64 KiB frames: 1 -> 5.88, 2 -> 5.19, 4 -> 5.6 .. 6.1 ms; gpurun_out/r03l)
+    uint32_t n = s ? (uint32_t)strtoul(s, nullptr, 10) : 2;
     return std::max<uint32_t>(1, std::min<uint32_t>(n, 256));
   }();
   return v;
@@ -287,7 +296,9 @@ DecodeResult GpuContext::decode(const void* dSrc, size_t srcSize, const HostFram
                            (uint32_t)(firstFrame + c.f0), c.n, firstFrame * info->frameSize, c.scratch, c.lay, c.st, tm);
         launches_ += 1;
       }
-      launches_ += launch_decode_rounds(dSrc, dDst, c.n, baseRounds, true, c.scratch, c.lay, c.st, tm);
+      static const bool sideHuf = [] { const char* e = getenv("ZRA_B200_SIDE_HUF"); return !e || atoi(e) != 0; }();
+      const SideLane* side = (single || !sideHuf || chunks.size() > (size_t)kPoolStreams) ? nullptr : &side_[c.idx % kPoolStreams];
+      launches_ += launch_decode_rounds(dSrc, dDst, c.n, baseRounds, true, c.scratch, c.lay, c.st, tm, side);
       if (!enqueue_tail(c)) return fail_cuda();
     }
     for (Chunk& c : chunks)

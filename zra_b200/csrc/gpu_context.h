@@ -123,6 +123,7 @@ class GpuContext {
   bool profiling_{false};
   static constexpr int kPoolStreams = 16;
   cudaStream_t pool_[kPoolStreams] = {};
+  SideLane side_[kPoolStreams];  // the chunks' Huffman stages run beside their sequence stages (decode_launch.h)
   cudaEvent_t forkEvent_{nullptr};
   // host-pointer calls: every upload goes through upStream_ and every download through downStream_, in chunk order
   // (copies issued on the chunks' own streams share the link and all finish late, which delays the first download)
