@@ -188,3 +188,37 @@ def system_zstd_decompress(data, cap):
     if L.ZSTD_isError(r):
         raise OracleError(1, int((1 << 64) - r))
     return out[:r]
+
+
+class _ZBuf(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("size", C.c_size_t), ("pos", C.c_size_t)]
+
+
+def system_zstd_decompress_stream(src, cap, feed=1 << 16):
+    """Stock libzstd 1.5.5 through its STREAMING decoder (ZSTD_decompressStream), which sizes its window and block
+    buffers from each frame header's Window_Descriptor and refuses offsets beyond it — unlike the one-shot call."""
+    L = C.CDLL("libzstd.so.1")
+    L.ZSTD_createDStream.restype = C.c_void_p
+    L.ZSTD_freeDStream.argtypes = [C.c_void_p]
+    L.ZSTD_decompressStream.argtypes = [C.c_void_p, C.POINTER(_ZBuf), C.POINTER(_ZBuf)]
+    L.ZSTD_decompressStream.restype = C.c_size_t
+    L.ZSTD_isError.argtypes = [C.c_size_t]
+    L.ZSTD_getErrorName.argtypes = [C.c_size_t]
+    L.ZSTD_getErrorName.restype = C.c_char_p
+    src = np.ascontiguousarray(src, dtype=np.uint8)
+    out = np.empty(max(cap, 1), np.uint8)
+    ds = L.ZSTD_createDStream()
+    try:
+        o = _ZBuf(out.ctypes.data, cap, 0)
+        at = 0
+        while at < src.size:
+            n = min(feed, src.size - at)
+            i = _ZBuf(src.ctypes.data + at, n, 0)
+            while i.pos < i.size:
+                r = L.ZSTD_decompressStream(ds, C.byref(o), C.byref(i))
+                if L.ZSTD_isError(r):
+                    raise RuntimeError("libzstd stream: " + L.ZSTD_getErrorName(r).decode())
+            at += n
+        return out[: o.pos]
+    finally:
+        L.ZSTD_freeDStream(ds)

@@ -125,3 +125,50 @@ def test_header_crc_verification_needs_no_gpu():
             assert not zra_b200.VerifyHeaderCrc(b), (name, at)
         with pytest.raises(zra_b200.ZraError):
             zra_b200.VerifyHeaderCrc(a[: h["size"] - 1])
+
+
+def _put40(a, at, v):
+    for i in range(5):
+        a[at + i] = (v >> (8 * i)) & 255
+
+
+def test_crafted_seek_tables_are_refused_before_any_gpu_work():
+    """the seek table is untrusted. Entries out of order, outside the requested range or longer than 4 GiB
+    must be refused with ZStdError / srcSize_wrong (72) BEFORE sizes are derived from them (these checks sit ahead of
+    the first GPU call, so this runs in the CPU tier); nothing may unwind through the C shim."""
+    archive, meta = golden_archive("text_f16384_l3")
+    h = parse_header(archive)
+    table = 38 + h["metaSize"]
+    reader = lambda a: (lambda off, size: a[off: off + size].tobytes())
+    fs = h["frameSize"]
+
+    def expect_72(fn):
+        with pytest.raises(zra_b200.ZraError) as e:
+            fn()
+        assert e.value.code == zra_b200.StatusCode.ZStdError and e.value.zstd_code == 72, (e.value.code, e.value.zstd_code)
+
+    # entry 2 below entry 1 (fb < fa)
+    bad = archive.copy()
+    _put40(bad, table + 5 * 2, 1)
+    expect_72(lambda: zra_b200.Decompressor(reader(bad)).Decompress(fs, 2 * fs))
+    expect_72(lambda: zra_b200.FullDecompressor(reader(bad)).Decompress(np.empty(4 * fs, np.uint8)))
+    # last entry of the range below the first (b < a): the compressed size would wrap
+    bad = archive.copy()
+    _put40(bad, table + 5 * 3, 0)
+    expect_72(lambda: zra_b200.Decompressor(reader(bad)).Decompress(2 * fs, fs))
+    # an inner entry beyond the end of the range
+    bad = archive.copy()
+    _put40(bad, table + 5 * 1, (1 << 39))
+    expect_72(lambda: zra_b200.Decompressor(reader(bad)).Decompress(0, 2 * fs))
+
+
+def test_crafted_header_geometry_is_refused_by_the_buffer_entry_points():
+    """metaSize / tableSize must describe a seek table that lies inside the header (the frame-parallel decoder
+    reads it; the reference's serial decoder never does): HeaderInvalid, not a wild host read."""
+    archive, meta = golden_archive("text_f16384_l3")
+    bad = archive.copy()
+    bad[34:38] = np.frombuffer((0x7FFFFFF0).to_bytes(4, "little"), np.uint8)   # metaSize
+    for fn in (lambda: zra_b200.DecompressBuffer(bad), lambda: zra_b200.DecompressRA(bad, 0, 100)):
+        with pytest.raises(zra_b200.ZraError) as e:
+            fn()
+        assert e.value.code in (zra_b200.StatusCode.HeaderInvalid, zra_b200.StatusCode.OutOfBoundsAccess), e.value.code

@@ -51,6 +51,23 @@ def check_archive(z, data, fs):
         assert np.array_equal(refzra.ref_decompress(z), data)
 
 
+@pytest.mark.parametrize("fs,lvl", [(4 << 20, 1), (4 << 20, 3), (3 << 20, 2), (1 << 20, 1), (65536, 3)])
+def test_large_frames_decode_with_a_streaming_zstd_decoder(fs, lvl):
+    """the matchers look anywhere in the frame, so the frame header must DECLARE a window that covers the
+    frame; a streaming decoder (zstd -d, ZSTD_decompressStream) sizes its buffers by it and refuses longer offsets."""
+    data = make("text", 2 * fs + 12345, fs)
+    z = zra_b200.CompressBuffer(data, lvl, fs, True)
+    got = refzra.system_zstd_decompress_stream(z, data.size)
+    assert np.array_equal(got, data)
+    # the declared window covers the frame
+    h = parse_header(z)
+    t = seek_table(z)
+    first = z[h["size"] + int(t[0]):]
+    assert first[4] & 0x20 == 0   # not single-segment: a window descriptor follows
+    wlog = (int(first[5]) >> 3) + 10
+    assert (1 << wlog) >= min(fs, data.size)
+
+
 @pytest.mark.parametrize("kind,n,fs,lvl,ck", [
     ("text", 1_000_003, 16384, 3, True),
     ("text", 4 << 20, 65536, 1, True),
@@ -166,3 +183,42 @@ def test_compression_is_deterministic(fs, lvl):
     for _ in range(3):
         again = zra_b200.CompressBuffer(data, lvl, fs, True)
         assert again.size == first.size and np.array_equal(again, first)
+
+
+@pytest.mark.parametrize("world,n,fs,lvl", [(2, 4 << 20, 65536, 3), (3, (6 << 20) + 12345, 65536, 1), (4, 1 << 20, 16384, 3), (2, (5 << 20), 262144, 3)])
+def test_sharded_compress_frames_stitch_into_one_archive(world, n, fs, lvl):
+    """SURVEY.md 8e / BASELINE configs[2] on ONE GPU: the input is cut into `world` contiguous frame ranges, each is
+    compressed by ZraCudaCompressFrames (what a rank does to its shard), the per-frame sizes are concatenated (what the
+    NCCL all-gather delivers) and the header is stitched by ZraShardBuildHeader. The stitched archive must equal, byte
+    for byte, the archive ZraCudaCompressBuffer makes of the whole input (frames are independent, the encoder is
+    deterministic), and the reference decoder and stock libzstd must accept it."""
+    import torch
+
+    from zra_b200 import shard
+
+    data = make("text", n, fs, seed=3)
+    ctx = zra_b200.CudaContext(0)
+    frames = (n + fs - 1) // fs
+    d_all = torch.zeros(n + 64, dtype=torch.uint8, device="cuda")
+    d_all[:n] = torch.from_numpy(data).cuda()
+    sizes, payloads = [], []
+    for r in range(world):
+        lo, hi = shard.byte_range(n, fs, r, world)
+        d_in = torch.zeros(hi - lo + 64, dtype=torch.uint8, device="cuda")
+        d_in[: hi - lo] = d_all[lo:hi]
+        cap = int(zra_b200.GetOutputBufferSize(hi - lo, fs))
+        d_out = torch.empty(cap + 64, dtype=torch.uint8, device="cuda")
+        s, produced = shard.compress_shard(ctx, d_in.data_ptr(), hi - lo, fs, lvl, True, d_out.data_ptr(), cap)
+        torch.cuda.synchronize()
+        f0, f1 = shard.frame_range(frames, r, world)
+        assert s.size == f1 - f0 and int(s.sum()) == produced
+        sizes.append(s)
+        payloads.append(d_out[:produced].cpu().numpy())
+    header = shard.build_header(n, fs, np.concatenate(sizes))
+    stitched = np.concatenate([header] + payloads)
+    whole_cap = int(zra_b200.GetOutputBufferSize(n, fs))
+    d_whole = torch.empty(whole_cap + 64, dtype=torch.uint8, device="cuda")
+    m = ctx.compress_buffer(d_all.data_ptr(), n, d_whole.data_ptr(), whole_cap, level=lvl, frame_size=fs, checksum=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(stitched, d_whole[:m].cpu().numpy()), "stitched shards differ from the one-piece archive"
+    check_archive(stitched, data, fs)

@@ -166,3 +166,60 @@ def test_sharded_random_access_over_gloo(world):
         p.join(timeout=60)
     assert sorted(r[0] for r in res) == list(range(world))
     assert all(r[1] for r in res), res
+
+
+def _reads_worker(rank, world, port, n, shard_bytes, rsz, q):
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        data = synth.text(n, seed=9, threads=1)
+        lo, hi = rank * shard_bytes, min(n, (rank + 1) * shard_bytes)
+        mine = torch.from_numpy(data[lo:hi].copy())
+        served = [0]
+
+        def serve(abs_off, sizes):
+            a, s = abs_off.tolist(), sizes.tolist()
+            assert all(lo <= o and o + z <= hi for o, z in zip(a, s)), "a piece outside this rank's shard"
+            served[0] += len(a)
+            return torch.cat([mine[o - lo: o - lo + z] for o, z in zip(a, s)]) if a else torch.empty(0, dtype=torch.uint8)
+
+        rng = np.random.default_rng(100 + rank)
+        cnt = 500
+        offs = rng.integers(0, n - rsz + 1, cnt).astype(np.int64)
+        # make sure some reads straddle every shard boundary
+        for b in range(1, world):
+            offs[b] = b * shard_bytes - 1 - rank
+            offs[world + b] = b * shard_bytes - rsz + 1
+        sr = shard.ShardedReads(n, shard_bytes, rsz)
+        got = sr.read(torch.from_numpy(offs), serve).numpy()
+        want = np.stack([data[o: o + rsz] for o in offs])
+        q.put((rank, bool(np.array_equal(got, want)), served[0]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_reads_all_to_all_over_gloo(world):
+    """The tensor data plane bench.py uses on NCCL (ShardedReads: all_to_all_single of offsets, then of bytes), on gloo:
+    every rank's reads into the whole archive come back bit-exact and in request order, boundary-crossing reads included."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    fs, rsz = 16384, 4096
+    shard_bytes = 20 * fs
+    n = world * shard_bytes - 1234     # the last shard is shorter
+    procs = [ctx.Process(target=_reads_worker, args=(r, world, port, n, shard_bytes, rsz, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(r[0] for r in res) == list(range(world))
+    assert all(r[1] for r in res), res
+    assert sum(r[2] for r in res) >= world * 500     # every read was served by somebody (crossing reads twice)

@@ -56,6 +56,9 @@ for suffix in ("_full", "_enc_full", "_ra_full"):
       kn = hdr.index("Kernel Name")
       with open(os.path.join(P, out_tag + "_ncu" + suffix + "_summary.csv"), "w") as f:
           names = [r[kn].split("(")[0].replace(", ", "_").replace(",", "_") for r in rows[2:]]
+          sys.path.insert(0, ROOT)
+          import bench  # the stamp bench.py checks before it trusts a capture's DRAM traffic
+          f.write("# source_sha256=" + bench.kernel_source_hash() + "\n")
           f.write("metric,unit," + ",".join(names) + "\n")
           for k in KEYS:
               if k in hdr:

@@ -58,7 +58,11 @@ ZRA_DEV EncParams enc_params(int level, u32 frameLen, bool checksum) {
   p.mls = L < 4 ? 4 : (L > 7 ? 7 : L);
   p.step = accel;
   p.checksum = checksum ? 1 : 0;
-  p.windowLogMax = W;
+  // The matchers look for candidates anywhere in the frame (a frame is its own window), so the DECLARED window must
+  // cover the whole frame (RFC 8878 3.1.1.1.2: no offset beyond Window_Size) even where the level's row has a smaller
+  // one — frames above 512 KiB / 1 MiB / 2 MiB at levels <= 1 / 2 / >= 3. One-shot decoders never looked, streaming
+  // decoders (zstd -d, ZSTD_decompressStream) size their buffers by it.
+  p.windowLogMax = W > srcLog ? W : (srcLog < 10 ? 10 : srcLog);
   return p;
 }
 

@@ -36,6 +36,9 @@ OpStatus host_decompress_archive(GpuContext* g, const uint8_t* archive, size_t n
   if (info.frames && !info.frameSize) return zra_error(3);
   if (info.frameSize && info.tableSize != table_entries(info.uncompressedSize, info.frameSize)) return zra_error(3);
   if (n < info.headerSize) return zra_error(5);
+  // the seek table is read below: it must lie where the header says, inside the header (a crafted metaSize would
+  // otherwise send the reads far outside the caller's buffer); same rule as the device path (zra_cuda_api.cu read_info)
+  if (38ull + info.metaSize + kEntrySize * (uint64_t)info.tableSize != info.headerSize) return zra_error(3);
   uint64_t lastEntry = get_le(archive + 38 + info.metaSize + kEntrySize * (size_t)(info.tableSize - 1), 5);
   if ((uint64_t)info.headerSize + lastEntry != n) return zra_error(1, 72);  // truncated or trailing bytes: srcSize_wrong
   if (!info.frames) return OpStatus{};
@@ -97,6 +100,8 @@ OpStatus host_decompress_range(GpuContext* g, const uint8_t* archive, size_t n, 
                                uint64_t size, uint8_t* out) {
   if (!info.frameSize) return zra_error(3);
   if (!size) return OpStatus{};
+  if (n < info.headerSize) return zra_error(5);
+  if (38ull + info.metaSize + kEntrySize * (uint64_t)info.tableSize != info.headerSize) return zra_error(3);  // (see above)
   const uint8_t* table = archive + 38 + info.metaSize;
   uint64_t first = offset / info.frameSize, last = (offset + size - 1) / info.frameSize + 1;
   if (last >= info.tableSize) return zra_error(5);

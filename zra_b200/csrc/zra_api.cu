@@ -194,9 +194,19 @@ namespace zra {
   }
 
   // ------------------------------------------------------------------ decompression (source/zra.cpp:243-302)
+  namespace {
+    // The frame-parallel decoder reads the seek table (the reference's serial decoder never does): the table must lie
+    // where the fixed header says, inside the header. Checked before any GPU work.
+    void check_table_geometry(const Header& h) {
+      const ArchiveInfo info = info_of(h);
+      if (kFixedHeaderSize + (u64)info.metaSize + kEntrySize * (u64)info.tableSize != info.headerSize) throw Exception(StatusCode::HeaderInvalid);
+    }
+  }  // namespace
+
   void DecompressBuffer(const BufferView& input, const BufferView& output) {
     Header header(input);
     if (output.size < header.uncompressedSize) throw Exception(StatusCode::OutputBufferTooSmall);
+    check_table_geometry(header);
     GpuContext* g = gpu();
     raise(host_decompress_archive(g, input.data, input.size, info_of(header), output.data), g);
   }
@@ -213,6 +223,7 @@ namespace zra {
     // `>=`: the reference's in-memory entry point cannot reach the last byte
     if (offset + size >= header.uncompressedSize) throw Exception(StatusCode::OutOfBoundsAccess);
     if (output.size < size) throw Exception(StatusCode::OutputBufferTooSmall);
+    check_table_geometry(header);
     GpuContext* g = gpu();
     raise(host_decompress_range(g, input.data, input.size, info_of(header), offset, size, output.data), g);
   }
@@ -307,6 +318,13 @@ namespace zra {
     u64 first = q, last = q + q2 + (r2 ? 1 : 0);
     if (last >= seekTable.size() / kEntrySize) throw Exception(StatusCode::OutOfBoundsAccess);  // table shorter than the geometry
     u64 a = entry_get(seekTable.data(), first), b = entry_get(seekTable.data(), last);
+    // the seek table is untrusted input: every entry of the range must lie inside it, in order, before any size is
+    // derived from it (a wrapped size would be a huge allocation, a wild upload range or an out-of-bounds kernel read)
+    if (b < a) throw Exception(StatusCode::ZStdError, 72);  // srcSize_wrong
+    for (u64 f = first; f < last; f++) {
+      const u64 fa = entry_get(seekTable.data(), f), fb = entry_get(seekTable.data(), f + 1);
+      if (fa < a || fb < fa || fb > b || fb - fa > 0xFFFFFFFFull) throw Exception(StatusCode::ZStdError, 72);
+    }
     size_t compressedSize = b - a;
 
     // The reference reads into `cache` (or a one-off buffer above maxCacheSize, zra.cpp:383-389); here the callback —
@@ -360,6 +378,11 @@ namespace zra {
     size_t cur = static_cast<size_t>(reinterpret_cast<u8*>(entry) - seekTable.data()) / kEntrySize;
     size_t lastIdx = std::min(entries ? entries - 1 : 0, cur + output.size / header.frameSize);
     u64 a = entry_get(seekTable.data(), cur), b = entry_get(seekTable.data(), lastIdx);
+    if (b < a) throw Exception(StatusCode::ZStdError, 72);  // untrusted seek table: see Decompressor::Decompress
+    for (size_t f = cur; f < lastIdx; f++) {
+      const u64 fa = entry_get(seekTable.data(), f), fb = entry_get(seekTable.data(), f + 1);
+      if (fa < a || fb < fa || fb > b || fb - fa > 0xFFFFFFFFull) throw Exception(StatusCode::ZStdError, 72);
+    }
     // one read callback per call, like the reference (zra.cpp:431-433), but into page-locked staging (see Decompressor)
     GpuContext* g = gpu();
     const size_t compressedSize = b - a;
@@ -393,6 +416,9 @@ namespace {
   ZraStatus make_status(ZraStatusCode zra, int zstd = 0) { return ZraStatus{zra, static_cast<int8_t>(zstd)}; }
   ZraStatus make_status(const zra::Exception& e) { return make_status(static_cast<ZraStatusCode>(e.code), e.zstdCode); }
   const ZraStatus kOk{Success, 0};
+  // nothing may unwind through the C ABI: a host failure (std::bad_alloc, std::length_error from a caller-supplied size)
+  // is reported as a zstd memory_allocation error (ZSTD_error_memory_allocation = 64)
+  const ZraStatus kHostFailure{ZStdError, 64};
 }  // namespace
 
 extern "C" {
@@ -407,14 +433,14 @@ ZraStatus ZraCreateHeader(ZraHeader** header, void (*readFunction)(size_t, size_
   try {
     *header = reinterpret_cast<ZraHeader*>(new zra::Header(readFunction));
     return kOk;
-  } catch (const zra::Exception& e) { return make_status(e); }
+  } catch (const zra::Exception& e) { return make_status(e); } catch (const std::exception&) { return kHostFailure; }
 }
 
 ZraStatus ZraCreateHeader2(ZraHeader** header, void* buffer, size_t size) {
   try {
     *header = reinterpret_cast<ZraHeader*>(new zra::Header(zra::BufferView(buffer, size)));
     return kOk;
-  } catch (const zra::Exception& e) { return make_status(e); }
+  } catch (const zra::Exception& e) { return make_status(e); } catch (const std::exception&) { return kHostFailure; }
 }
 
 void ZraDeleteHeader(ZraHeader* header) { delete reinterpret_cast<zra::Header*>(header); }
@@ -440,7 +466,7 @@ ZraStatus ZraCompressBuffer(void* inputBuffer, size_t inputSize, void* outputBuf
                                       zra::BufferView(outputBuffer, zra::GetOutputBufferSize(inputSize, frameSize)), compressionLevel,
                                       frameSize, checksum, zra::BufferView(metaBuffer, metaSize));
     return kOk;
-  } catch (const zra::Exception& e) { return make_status(e); }
+  } catch (const zra::Exception& e) { return make_status(e); } catch (const std::exception&) { return kHostFailure; }
 }
 
 ZraStatus ZraDecompressBuffer(void* inputBuffer, size_t inputSize, void* outputBuffer) {
@@ -448,14 +474,14 @@ ZraStatus ZraDecompressBuffer(void* inputBuffer, size_t inputSize, void* outputB
     size_t cap = inputSize >= 26 ? zrab::get_le(static_cast<uint8_t*>(inputBuffer) + 18, 8) : 0;
     zra::DecompressBuffer(zra::BufferView(inputBuffer, inputSize), zra::BufferView(outputBuffer, cap));
     return kOk;
-  } catch (const zra::Exception& e) { return make_status(e); }
+  } catch (const zra::Exception& e) { return make_status(e); } catch (const std::exception&) { return kHostFailure; }
 }
 
 ZraStatus ZraDecompressRA(void* inputBuffer, size_t inputSize, void* outputBuffer, size_t offset, size_t size) {
   try {
     zra::DecompressRA(zra::BufferView(inputBuffer, inputSize), zra::BufferView(outputBuffer, size), offset, size);
     return kOk;
-  } catch (const zra::Exception& e) { return make_status(e); }
+  } catch (const zra::Exception& e) { return make_status(e); } catch (const std::exception&) { return kHostFailure; }
 }
 
 ZraStatus ZraCreateCompressor(ZraCompressor** compressor, size_t size, int8_t compressionLevel, uint32_t frameSize, bool checksum,
@@ -464,7 +490,7 @@ ZraStatus ZraCreateCompressor(ZraCompressor** compressor, size_t size, int8_t co
     *compressor = reinterpret_cast<ZraCompressor*>(
         new zra::Compressor(size, compressionLevel, frameSize, checksum, zra::BufferView(metaBuffer, metaSize)));
     return kOk;
-  } catch (const zra::Exception& e) { return make_status(e); }
+  } catch (const zra::Exception& e) { return make_status(e); } catch (const std::exception&) { return kHostFailure; }
 }
 
 void ZraDeleteCompressor(ZraCompressor* compressor) { delete reinterpret_cast<zra::Compressor*>(compressor); }
@@ -479,7 +505,7 @@ ZraStatus ZraCompressWithCompressor(ZraCompressor* compressor, void* inputBuffer
     auto* c = reinterpret_cast<zra::Compressor*>(compressor);
     *outputSize = c->Compress(zra::BufferView(inputBuffer, inputSize), zra::BufferView(outputBuffer, c->GetOutputBufferSize(inputSize)));
     return kOk;
-  } catch (const zra::Exception& e) { return make_status(e); }
+  } catch (const zra::Exception& e) { return make_status(e); } catch (const std::exception&) { return kHostFailure; }
 }
 
 size_t ZraGetHeaderSizeWithCompressor(ZraCompressor* compressor) { return reinterpret_cast<zra::Compressor*>(compressor)->GetHeaderSize(); }
@@ -489,14 +515,14 @@ ZraStatus ZraGetHeaderWithCompressor(ZraCompressor* compressor, void* outputBuff
     const auto& header = reinterpret_cast<zra::Compressor*>(compressor)->GetHeader();
     std::memcpy(outputBuffer, header.data(), header.size());
     return kOk;
-  } catch (const zra::Exception& e) { return make_status(e); }
+  } catch (const zra::Exception& e) { return make_status(e); } catch (const std::exception&) { return kHostFailure; }
 }
 
 ZraStatus ZraCreateDecompressor(ZraDecompressor** decompressor, void (*readFunction)(size_t, size_t, void*), size_t maxCacheSize) {
   try {
     *decompressor = reinterpret_cast<ZraDecompressor*>(new zra::Decompressor(readFunction, maxCacheSize));
     return kOk;
-  } catch (const zra::Exception& e) { return make_status(e); }
+  } catch (const zra::Exception& e) { return make_status(e); } catch (const std::exception&) { return kHostFailure; }
 }
 
 void ZraDeleteDecompressor(ZraDecompressor* decompressor) { delete reinterpret_cast<zra::Decompressor*>(decompressor); }
@@ -509,7 +535,7 @@ ZraStatus ZraDecompressWithDecompressor(ZraDecompressor* decompressor, size_t of
   try {
     reinterpret_cast<zra::Decompressor*>(decompressor)->Decompress(offset, size, zra::BufferView(outputBuffer, size));
     return kOk;
-  } catch (const zra::Exception& e) { return make_status(e); }
+  } catch (const zra::Exception& e) { return make_status(e); } catch (const std::exception&) { return kHostFailure; }
 }
 
 // maxCacheSize is accepted and ignored, exactly like the reference (source/zra.cpp:602-604)
@@ -517,7 +543,7 @@ ZraStatus ZraCreateFullDecompressor(ZraFullDecompressor** decompressor, void (*r
   try {
     *decompressor = reinterpret_cast<ZraFullDecompressor*>(new zra::FullDecompressor(readFunction));
     return kOk;
-  } catch (const zra::Exception& e) { return make_status(e); }
+  } catch (const zra::Exception& e) { return make_status(e); } catch (const std::exception&) { return kHostFailure; }
 }
 
 void ZraDeleteFullDecompressor(ZraFullDecompressor* decompressor) { delete reinterpret_cast<zra::FullDecompressor*>(decompressor); }
@@ -531,7 +557,7 @@ ZraStatus ZraDecompressWithFullDecompressor(ZraFullDecompressor* decompressor, v
   try {
     *outputSize = reinterpret_cast<zra::FullDecompressor*>(decompressor)->Decompress(zra::BufferView(outputBuffer, outputCapacity));
     return kOk;
-  } catch (const zra::Exception& e) { return make_status(e); }
+  } catch (const zra::Exception& e) { return make_status(e); } catch (const std::exception&) { return kHostFailure; }
 }
 
 }  // extern "C"

@@ -139,3 +139,93 @@ def sharded_random_access(offsets, sizes, uncompressed_size, frame_size, serve, 
             out[at: at + n] = blob[cur: cur + n]
             cur += n
     return out
+
+
+# ---------------------------------------------------------------------------- the same exchange as tensors
+class ShardedReads:
+    """Data plane of batched random access over an archive whose frames are sharded contiguously across the ranks
+    (BASELINE configs[3]): fixed-size reads are routed to the owners of their bytes with
+    torch.distributed.all_to_all_single (NCCL on GPUs, gloo in the CPU tests), served there from the resident shard
+    (`serve`: on a GPU, ZraCudaDecompressRABatch on the shard's own archive) and the bytes come back the same way, in the
+    caller's request order. Everything stays a tensor on `device`; nothing is pickled.
+
+    Shards cover equal byte ranges (`shard_bytes` each, a multiple of the frame size), the last one may be shorter. A
+    read that crosses a shard boundary is split into one piece per shard (rare: handled by a second, tiny exchange).
+    Bounds are the streaming twin's: offset + size <= uncompressedSize (source/zra.cpp:370)."""
+
+    def __init__(self, uncompressed_size, shard_bytes, read_size, group=None, device="cpu"):
+        import torch.distributed as dist
+
+        self.U, self.S, self.R = int(uncompressed_size), int(shard_bytes), int(read_size)
+        self.group, self.dev = group, device
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+
+    def _exchange(self, send, send_counts, width):
+        """all_to_all of rows: `send` is [n, width] sorted by destination, send_counts[w] rows go to rank w."""
+        import torch
+        import torch.distributed as dist
+
+        sc = torch.as_tensor(send_counts, dtype=torch.int64, device=self.dev)
+        rc = torch.empty_like(sc)
+        dist.all_to_all_single(rc, sc, group=self.group)
+        rcl, scl = [int(x) for x in rc.tolist()], [int(x) for x in sc.tolist()]
+        recv = torch.empty((sum(rcl), width), dtype=send.dtype, device=self.dev)
+        dist.all_to_all_single(recv.view(-1), send.reshape(-1), output_split_sizes=[c * width for c in rcl],
+                               input_split_sizes=[c * width for c in scl], group=self.group)
+        return recv, rcl
+
+    def read(self, offsets, serve):
+        """offsets: int64 tensor [n] on `device` (absolute offsets into the whole archive). serve(abs_offsets, sizes) ->
+        uint8 tensor with the pieces back to back, for pieces inside this rank's shard (tensors on `device`).
+        Returns a uint8 tensor [n, read_size]."""
+        import torch
+
+        n, R, S, W = int(offsets.numel()), self.R, self.S, self.world
+        if n and (int(offsets.min()) < 0 or int(offsets.max()) + R > self.U):
+            raise binding.ZraError(binding.StatusCode.OutOfBoundsAccess)
+        out = torch.empty((n, R), dtype=torch.uint8, device=self.dev)
+        owner = torch.div(offsets, S, rounding_mode="floor")
+        crossing = torch.div(offsets + (R - 1), S, rounding_mode="floor") != owner
+        # ---- whole reads: one row of [offset] per read, sorted by owner; the answers come back in the same order
+        idx = torch.nonzero(~crossing).view(-1)
+        order = torch.argsort(owner[idx], stable=True)
+        idx = idx[order]
+        counts = torch.bincount(owner[idx], minlength=W)[:W].tolist()
+        req, rcl = self._exchange(offsets[idx].view(-1, 1), counts, 1)
+        m = int(req.shape[0])
+        sizes = torch.full((m,), R, dtype=torch.int64, device=self.dev)
+        served = serve(req.view(-1), sizes) if m else torch.empty(0, dtype=torch.uint8, device=self.dev)
+        back, _ = self._exchange(served.view(m, R), rcl, R)
+        out[idx] = back
+        # ---- reads that cross a shard boundary: two pieces each (a read is shorter than a shard)
+        cidx = torch.nonzero(crossing).view(-1)
+        k = int(cidx.numel())
+        total_cross = torch.tensor([k], dtype=torch.int64, device=self.dev)
+        import torch.distributed as dist
+        dist.all_reduce(total_cross, group=self.group)
+        if int(total_cross.item()):
+            o = offsets[cidx]
+            first = (owner[cidx] + 1) * S - o                      # bytes in the owner's shard
+            po = torch.cat([o, o + first])                          # piece offsets
+            ps = torch.cat([first, R - first])                      # piece sizes
+            pw = torch.cat([owner[cidx], owner[cidx] + 1])         # piece owners
+            pr = torch.cat([torch.arange(k, device=self.dev), torch.arange(k, device=self.dev)])
+            pin = torch.cat([torch.zeros(k, dtype=torch.int64, device=self.dev), first])   # offset inside the read
+            order = torch.argsort(pw, stable=True)
+            po, ps, pw, pr, pin = po[order], ps[order], pw[order], pr[order], pin[order]
+            counts = torch.bincount(pw, minlength=W)[:W].tolist() if k else [0] * W
+            req, rcl = self._exchange(torch.stack([po, ps], dim=1) if k else torch.empty((0, 2), dtype=torch.int64, device=self.dev), counts, 2)
+            m = int(req.shape[0])
+            served = serve(req[:, 0].contiguous(), req[:, 1].contiguous()) if m else torch.empty(0, dtype=torch.uint8, device=self.dev)
+            # pieces have different sizes: pad every piece to a row of R bytes for the way back
+            rows = torch.zeros((m, R), dtype=torch.uint8, device=self.dev)
+            at = 0
+            for i in range(m):
+                s = int(req[i, 1])
+                rows[i, :s] = served[at: at + s]
+                at += s
+            back, _ = self._exchange(rows, rcl, R)
+            for i in range(int(pr.numel())):
+                s, a = int(ps[i]), int(pin[i])
+                out[cidx[pr[i]], a: a + s] = back[i, :s]
+        return out
