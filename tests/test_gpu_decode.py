@@ -252,7 +252,7 @@ def test_corruption_matches_oracle():
             got = (int(e.code), e.zstd_code)
         assert (got is None) == (ora is None), (pos, got, ora)
         exact += got == ora
-    assert exact >= 36
+    assert exact >= 38   # the known divergence: a literals section declared larger than the frame is refused before its Huffman streams are read (70 where zstd may report 20)
     bad = archive.copy()
     bad[8] ^= 1
     with pytest.raises(zra_b200.ZraError) as e:

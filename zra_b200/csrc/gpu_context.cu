@@ -330,8 +330,12 @@ DecodeResult GpuContext::decode(const void* dSrc, size_t srcSize, const HostFram
         if (check(cudaMemcpy(&code, c.scratch + o, 4, cudaMemcpyDeviceToHost), "status readback")) return fail_cuda();
         for (Chunk& rest : chunks) cudaStreamSynchronize(rest.st);
         if (ordered) cudaStreamSynchronize(downStream_);
-        res.zstd = (int)code;
         res.failedFrame = (uint32_t)(c.f0 + c.summary[0]);
+        // The reference decodes a range of frames with ZSTD_decompressMultiFrame, which reports an unknown magic
+        // number AFTER a frame that decoded as srcSize_wrong ("following bytes are garbage", zstd_decompress.c:773-781):
+        // the lowest failing frame's prefix_unknown (10) becomes 72 unless it is the first frame of the call.
+        if (code == 10u && res.failedFrame > 0) code = 72u;
+        res.zstd = (int)code;
         return res;
       }
       if (frameSizes) {
