@@ -351,3 +351,54 @@ print("ok")
     r = subprocess.run([sys.executable, "-c", code], env={**os.environ, **env}, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
                        text=True, timeout=600)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-1500:]
+
+
+def test_full_decompressor_read_ahead(torch_cuda):
+    """FullDecompressor reads the NEXT call's bytes through the user's callback while the GPU works on this call
+    (SURVEY.md 8f-1). Same total number of callbacks and the same ranges as the reference's callback-per-call loop, each
+    range read exactly once when the caller keeps its buffer size; a caller that changes it, and two decompressors
+    interleaved on one thread (they share the thread's staging buffers), still get the right bytes."""
+    archive, meta = golden_archive("text_f16384_l3")
+    full = refzra.oracle_decompress_buffer(archive)
+    fs = meta["frameSize"]
+    calls = []
+
+    def reader(off, size):
+        calls.append((off, size))
+        return archive[off: off + size].tobytes()
+
+    def drain(fd, sizes):
+        pieces, i = [], 0
+        while True:
+            out = np.empty(sizes[i % len(sizes)], np.uint8)
+            i += 1
+            k = fd.Decompress(out)
+            if not k:
+                return np.concatenate(pieces)
+            pieces.append(out[:k].copy())
+
+    # steady buffer size: every compressed byte is read exactly once, in order
+    calls.clear()
+    fd = zra_b200.FullDecompressor(reader)
+    hdr_calls = len(calls)
+    assert np.array_equal(drain(fd, [3 * fs]), full)
+    data_calls = [c for c in calls[hdr_calls:] if c[1]]
+    assert [c[0] for c in data_calls] == sorted(c[0] for c in data_calls)
+    assert sum(c[1] for c in data_calls) == archive.size - parse_header(archive)["size"]
+    # a caller that changes its buffer size between calls: a read-ahead that does not fit is dropped, bytes stay right
+    assert np.array_equal(drain(zra_b200.FullDecompressor(reader), [3 * fs, fs, 5 * fs + 7, 2 * fs]), full)
+    # two decompressors interleaved on one thread
+    a, b = zra_b200.FullDecompressor(reader), zra_b200.FullDecompressor(reader)
+    pa, pb = [], []
+    oa, ob = np.empty(2 * fs, np.uint8), np.empty(3 * fs, np.uint8)
+    done_a = done_b = False
+    while not (done_a and done_b):
+        if not done_a:
+            k = a.Decompress(oa)
+            done_a = k == 0
+            pa.append(oa[:k].copy())
+        if not done_b:
+            k = b.Decompress(ob)
+            done_b = k == 0
+            pb.append(ob[:k].copy())
+    assert np.array_equal(np.concatenate(pa), full) and np.array_equal(np.concatenate(pb), full)

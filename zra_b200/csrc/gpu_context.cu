@@ -68,7 +68,7 @@ GpuContext::~GpuContext() {
   if (upStream_) cudaStreamDestroy(upStream_);
   if (downStream_) cudaStreamDestroy(downStream_);
   if (summaryHost_) cudaFreeHost(summaryHost_);
-  if (pinnedStage_) cudaFreeHost(pinnedStage_);
+  for (uint8_t* p : pinnedStage_) if (p) cudaFreeHost(p);
   if (stream_) cudaStreamDestroy(stream_);
 }
 
@@ -113,13 +113,15 @@ void* GpuContext::ensure(DevBuf& b, size_t bytes) {
   return b.p;
 }
 
-uint8_t* GpuContext::pinned_stage(size_t bytes) {
-  if (bytes <= pinnedStageCap_ && pinnedStage_) return pinnedStage_;
+uint8_t* GpuContext::pinned_stage(size_t bytes, int which) {
+  which &= 1;
+  stageGen_[which]++;
+  if (bytes <= pinnedStageCap_[which] && pinnedStage_[which]) return pinnedStage_[which];
   bind();
-  if (pinnedStage_) {
-    cudaFreeHost(pinnedStage_);
-    pinnedStage_ = nullptr;
-    pinnedStageCap_ = 0;
+  if (pinnedStage_[which]) {
+    cudaFreeHost(pinnedStage_[which]);
+    pinnedStage_[which] = nullptr;
+    pinnedStageCap_[which] = 0;
   }
   size_t want = std::max<size_t>(bytes + bytes / 4, 1 << 20);
   void* p = nullptr;
@@ -127,9 +129,9 @@ uint8_t* GpuContext::pinned_stage(size_t bytes) {
     want = std::max<size_t>(bytes, 1);
     if (check(cudaMallocHost(&p, want), "cudaMallocHost")) return nullptr;
   }
-  pinnedStage_ = static_cast<uint8_t*>(p);
-  pinnedStageCap_ = want;
-  return pinnedStage_;
+  pinnedStage_[which] = static_cast<uint8_t*>(p);
+  pinnedStageCap_[which] = want;
+  return pinnedStage_[which];
 }
 
 static size_t scratch_budget() {
@@ -303,6 +305,7 @@ DecodeResult GpuContext::decode(const void* dSrc, size_t srcSize, const HostFram
     }
     for (Chunk& c : chunks)
       if (!enqueue_download(c)) return fail_cuda();
+    if (io && io->whileBusy && g0 == 0) (*io->whileBusy)();  // everything of this group is queued: the GPU works, the caller reads ahead
     // ---- join, then look at every chunk's summary (in frame order, so the lowest failing frame wins)
     if (tm && timeline) {
       for (Chunk& c : chunks) cudaStreamSynchronize(c.st);

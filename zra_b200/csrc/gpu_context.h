@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -37,6 +38,9 @@ struct HostStaging {
   uint8_t* hostDst{nullptr};        // receives device output bytes [dstSkip, dstSkip + dstSize)
   uint64_t dstSkip{0};
   uint64_t dstSize{~0ull};
+  // called once on the caller's thread after the first group's work is queued and before it is waited for (the streaming
+  // classes read the NEXT call's bytes through the user's callback here, beside the GPU work of this call)
+  const std::function<void()>* whileBusy{nullptr};
 };
 
 // Parsed fixed header of a ZRA archive (source/zra.cpp:111-134 layout).
@@ -68,7 +72,9 @@ class GpuContext {
   void* ensure(DevBuf& b, size_t bytes);
   // Page-locked host staging that the streaming classes hand to the user's read callback, so that the compressed
   // bytes land where the upload can start from at link speed (grown geometrically, kept for the context's lifetime).
-  uint8_t* pinned_stage(size_t bytes);
+  uint8_t* pinned_stage(size_t bytes, int which = 0);  // two buffers: this call's bytes and the read-ahead of the next
+  // bumped every time a buffer is handed out: a reader that parked bytes in one can tell whether anybody asked for it since
+  uint64_t stage_gen(int which) const { return stageGen_[which & 1]; }
   DevBuf scratch, stageIn, stageOut, misc;
   DevBuf raSlotOf, raUnique, raDescs, raFrames;  // batched random access (ra_context.cu)
 
@@ -131,8 +137,9 @@ class GpuContext {
   std::vector<cudaEvent_t> upEvents_, doneEvents_;
   bool ensure_events(size_t n);
   uint32_t* summaryHost_{nullptr};  // pinned, 4 words per chunk
-  uint8_t* pinnedStage_{nullptr};
-  size_t pinnedStageCap_{0};
+  uint8_t* pinnedStage_[2] = {nullptr, nullptr};
+  size_t pinnedStageCap_[2] = {0, 0};
+  uint64_t stageGen_[2] = {0, 0};
   uint32_t* raHost_{nullptr};       // pinned, {unique frames, first bad request}
   uint64_t raSlotFrames_{0};        // entries of raSlotOf that are initialised to "empty"
   static constexpr uint32_t kMaxChunks = 1024;

@@ -74,7 +74,7 @@ OpStatus host_decompress_archive(GpuContext* g, const uint8_t* archive, size_t n
 }
 
 OpStatus host_decode_frames(GpuContext* g, const uint8_t* src, size_t srcSize, const HostFrame* frames, size_t nFrames,
-                            uint32_t frameSize, uint64_t skip, uint64_t size, uint8_t* out) {
+                            uint32_t frameSize, uint64_t skip, uint64_t size, uint8_t* out, const std::function<void()>* whileBusy) {
   if (!nFrames) return OpStatus{};
   cudaStream_t st = g->stream();
   uint64_t staged = 0;
@@ -93,6 +93,7 @@ OpStatus host_decode_frames(GpuContext* g, const uint8_t* src, size_t srcSize, c
   io.hostDst = out;
   io.dstSkip = skip;
   io.dstSize = size;
+  io.whileBusy = whileBusy;
   return from_decode(g->decode(dIn, srcSize, frames, nullptr, 0, nFrames, maxCap, dOut, nullptr, st, &io));
 }
 

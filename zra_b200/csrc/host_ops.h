@@ -1,5 +1,6 @@
 // host_ops.h — host-buffer operations behind the zra:: API (internal): stage, launch, copy back.
 #pragma once
+#include <functional>
 #include <cstddef>
 #include <cstdint>
 
@@ -23,7 +24,8 @@ OpStatus host_decompress_range(GpuContext* g, const uint8_t* archive, size_t n, 
 // Decodes `nFrames` frames found in src (host) into a device staging area laid out by frames[].dstOff,
 // then copies staging bytes [skip, skip+size) to out (host).
 OpStatus host_decode_frames(GpuContext* g, const uint8_t* src, size_t srcSize, const HostFrame* frames, size_t nFrames,
-                            uint32_t frameSize, uint64_t skip, uint64_t size, uint8_t* out);
+                            uint32_t frameSize, uint64_t skip, uint64_t size, uint8_t* out,
+                            const std::function<void()>* whileBusy = nullptr);
 
 // Complete archive from `in` (host) into `out` (host). Mirrors zra::CompressBuffer incl. its metadata quirk.
 OpStatus host_compress_buffer(GpuContext* g, const uint8_t* in, size_t n, uint8_t* out, size_t outCap, size_t* written, int level,

@@ -25,7 +25,17 @@ namespace zra {
     i8 level{};
     bool checksum{true};
   };
-  class ZDCtx {};
+  // (ZDCtx also carries FullDecompressor's read-ahead: the class layout of zra.hpp is the drop-in contract and has no
+  // room for it)
+  class ZDCtx {
+   public:
+    bool aheadValid{false};
+    size_t aheadCur{0}, aheadLast{0};   // seek-table range [cur, last] the read-ahead covers
+    u64 aheadA{0}, aheadB{0};           // its compressed byte range
+    int aheadBuf{0};                    // which pinned staging buffer holds it
+    uint64_t aheadGen{0};               // that buffer's hand-out count after the read-ahead (another reader on this thread bumps it)
+    int nextBuf{0};                     // buffer of the next call that reads for itself
+  };
 
   struct Entry {
     u8 bytes[5];
@@ -378,17 +388,36 @@ namespace zra {
     size_t cur = static_cast<size_t>(reinterpret_cast<u8*>(entry) - seekTable.data()) / kEntrySize;
     size_t lastIdx = std::min(entries ? entries - 1 : 0, cur + output.size / header.frameSize);
     u64 a = entry_get(seekTable.data(), cur), b = entry_get(seekTable.data(), lastIdx);
-    if (b < a) throw Exception(StatusCode::ZStdError, 72);  // untrusted seek table: see Decompressor::Decompress
-    for (size_t f = cur; f < lastIdx; f++) {
-      const u64 fa = entry_get(seekTable.data(), f), fb = entry_get(seekTable.data(), f + 1);
-      if (fa < a || fb < fa || fb > b || fb - fa > 0xFFFFFFFFull) throw Exception(StatusCode::ZStdError, 72);
-    }
-    // one read callback per call, like the reference (zra.cpp:431-433), but into page-locked staging (see Decompressor)
+    auto check_range = [&](size_t c0, size_t c1, u64 lo, u64 hi) {  // untrusted seek table: see Decompressor::Decompress
+      if (hi < lo) throw Exception(StatusCode::ZStdError, 72);
+      for (size_t f = c0; f < c1; f++) {
+        const u64 fa = entry_get(seekTable.data(), f), fb = entry_get(seekTable.data(), f + 1);
+        if (fa < lo || fb < fa || fb > hi || fb - fa > 0xFFFFFFFFull) throw Exception(StatusCode::ZStdError, 72);
+      }
+    };
+    check_range(cur, lastIdx, a, b);
+    // One read callback per call, like the reference (zra.cpp:431-433), into page-locked staging (see Decompressor) —
+    // but the callback that fills a call's bytes usually ran during the PREVIOUS call: the reference's loop is callback,
+    // decode, callback, decode on one thread, and with the decode on the GPU the host would sit idle in one half and the
+    // GPU in the other. So while this call's uploads / kernels / downloads run, the NEXT call's range (same output
+    // capacity assumed: the class is a sequential reader) is read ahead through the same callback, on the caller's
+    // thread, into the second staging buffer. A call whose range is not the one read ahead reads for itself.
+    // ZRA_B200_NO_READAHEAD=1 restores the strict callback-per-call order.
     GpuContext* g = gpu();
     const size_t compressedSize = b - a;
-    u8* input = g->pinned_stage(compressedSize);
-    if (!input) { cache.resize(compressedSize); input = cache.data(); }
-    readFunction(header.size + a, compressedSize, input);
+    static const bool readAhead = getenv("ZRA_B200_NO_READAHEAD") == nullptr;
+    u8* input;
+    if (ctx->aheadValid && ctx->aheadCur == cur && ctx->aheadLast == lastIdx && ctx->aheadA == a && ctx->aheadB == b &&
+        g->stage_gen(ctx->aheadBuf) == ctx->aheadGen) {
+      input = g->pinned_stage(compressedSize, ctx->aheadBuf);
+      ctx->nextBuf = ctx->aheadBuf ^ 1;
+    } else {
+      input = g->pinned_stage(compressedSize, ctx->nextBuf);
+      if (!input) { cache.resize(compressedSize); input = cache.data(); }
+      readFunction(header.size + a, compressedSize, input);
+      ctx->nextBuf ^= 1;
+    }
+    ctx->aheadValid = false;
     entry = reinterpret_cast<Entry*>(seekTable.data() + kEntrySize * lastIdx);
     if (lastIdx == cur) return 0;
 
@@ -406,7 +435,27 @@ namespace zra {
       d.pad = 0;
       total += d.dstCap;
     }
-    raise(host_decode_frames(g, input, compressedSize, frames.data(), frames.size(), header.frameSize, 0, total, output.data), g);
+    // the next call's range, if there is one
+    const size_t nCur = lastIdx, nLast = std::min(entries ? entries - 1 : 0, nCur + output.size / header.frameSize);
+    std::function<void()> ahead = [&]() {
+      // runs while this call's GPU work is in flight: nothing may unwind from here (a bad range or a throwing callback
+      // simply leaves no read-ahead; the next call reads for itself and reports it)
+      try {
+        const u64 na = entry_get(seekTable.data(), nCur), nb = entry_get(seekTable.data(), nLast);
+        check_range(nCur, nLast, na, nb);
+        u8* buf = g->pinned_stage(nb - na, ctx->nextBuf);
+        if (!buf) return;
+        readFunction(header.size + na, nb - na, buf);
+        ctx->aheadCur = nCur; ctx->aheadLast = nLast; ctx->aheadA = na; ctx->aheadB = nb; ctx->aheadBuf = ctx->nextBuf;
+        ctx->aheadGen = g->stage_gen(ctx->nextBuf);
+        ctx->aheadValid = true;
+      } catch (...) {
+        ctx->aheadValid = false;
+      }
+    };
+    const bool doAhead = readAhead && nLast > nCur && input != cache.data();
+    raise(host_decode_frames(g, input, compressedSize, frames.data(), frames.size(), header.frameSize, 0, total, output.data,
+                             doAhead ? &ahead : nullptr), g);
     return total;
   }
 }  // namespace zra
