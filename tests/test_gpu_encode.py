@@ -222,3 +222,36 @@ def test_sharded_compress_frames_stitch_into_one_archive(world, n, fs, lvl):
     torch.cuda.synchronize()
     assert np.array_equal(stitched, d_whole[:m].cpu().numpy()), "stitched shards differ from the one-piece archive"
     check_archive(stitched, data, fs)
+
+
+def _block_types(frame):
+    """Block types of one zstd frame (no dictionary, window descriptor present)."""
+    fhd = int(frame[4])
+    assert fhd & 0x20 == 0 and fhd >> 6 == 0 and fhd & 3 == 0
+    pos, types = 6, []
+    while True:
+        bh = int(frame[pos]) | int(frame[pos + 1]) << 8 | int(frame[pos + 2]) << 16
+        last, btype, bsize = bh & 1, (bh >> 1) & 3, bh >> 3
+        types.append(btype)
+        pos += 3 + (1 if btype == 1 else bsize)
+        if last:
+            return types
+
+
+def test_rle_blocks_follow_the_reference_rule():
+    """zstd_compress.c:2453-2464: a block of one repeated byte becomes an RLE block (type 1) — except the first block of a
+    frame. 512 KiB frames of zeros: block 0 compressed, blocks 1..3 RLE; the reference and stock libzstd decode it."""
+    fs = 512 << 10
+    data = np.zeros(2 * fs + 1000, np.uint8)
+    data[fs + 200_000:fs + 200_010] = 7          # the second frame's block 1 is NOT constant
+    z = zra_b200.CompressBuffer(data, 3, fs, True)
+    check_archive(z, data, fs)
+    h, t = parse_header(z), seek_table(z)
+    f0 = z[h["size"] + int(t[0]): h["size"] + int(t[1])]
+    f1 = z[h["size"] + int(t[1]): h["size"] + int(t[2])]
+    assert _block_types(f0) == [2, 1, 1, 1]
+    assert _block_types(f1) == [2, 2, 1, 1]
+    if refzra.have_ref():   # the reference makes the same choice
+        zr = refzra.ref_compress(data, 3, fs, True)
+        hr, tr = parse_header(zr), seek_table(zr)
+        assert _block_types(zr[hr["size"] + int(tr[0]): hr["size"] + int(tr[1])]) == [2, 1, 1, 1]

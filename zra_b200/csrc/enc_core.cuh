@@ -510,11 +510,21 @@ ZRA_DEV void enc_assemble(const u8* base, u64 fbase, const EncParams& p, EncCtx&
   const u32 seqSection = c.seqHeaderSize + c.seqStreamSize;
   const u32 cSize = litSection + seqSection;
   const u32 minGain = (c.blkLen >> 6) + 2;
-  const bool raw = c.blkLen < 7 || cSize + minGain >= c.blkLen || cSize >= kBlockSizeMax || c.seqStreamSize > s.seqOutCap;
-  const u32 bsize = raw ? c.blkLen : cSize;
-  const u32 bh = (c.lastBlock ? 1u : 0u) | ((raw ? 0u : 2u) << 1) | (bsize << 3);
+  bool raw = c.blkLen < 7 || cSize + minGain >= c.blkLen || cSize >= kBlockSizeMax || c.seqStreamSize > s.seqOutCap;
+  // RLE block, the reference's rule (zstd_compress.c:2453-2464): not the first block, "maybe RLE" sequence store, all bytes equal
+  bool rleBlock = false;
+  if (c.blkPos != 0 && c.nbSeq < 4 && c.litSize < 10 && c.blkLen > 0) {
+    rleBlock = true;
+    for (u32 k = 1; k < c.blkLen; k++) rleBlock &= base[fbase + c.blkPos + k] == base[fbase + c.blkPos];
+  }
+  if (rleBlock) raw = false;
+  const u32 bsize = (raw || rleBlock) ? c.blkLen : cSize;
+  const u32 bh = (c.lastBlock ? 1u : 0u) | ((rleBlock ? 1u : (raw ? 0u : 2u)) << 1) | (bsize << 3);
   out[op++] = (u8)bh; out[op++] = (u8)(bh >> 8); out[op++] = (u8)(bh >> 16);
-  if (raw) {
+  if (rleBlock) {
+    out[op++] = base[fbase + c.blkPos];
+    c.rep[0] = c.repSave[0]; c.rep[1] = c.repSave[1]; c.rep[2] = c.repSave[2];
+  } else if (raw) {
     for (u32 k = 0; k < c.blkLen; k++) out[op++] = base[fbase + c.blkPos + k];
     // a raw block carries no sequences: undo the repeat-offset updates the matcher made for it
     c.rep[0] = c.repSave[0]; c.rep[1] = c.repSave[1]; c.rep[2] = c.repSave[2];

@@ -878,11 +878,23 @@ __global__ void __launch_bounds__(256) k_enc_assemble_warp(EncJob j, EncView v) 
   const u32 seqSection = c.seqHeaderSize + c.seqStreamSize;
   const u32 cSize = litSection + seqSection;
   const u32 minGain = (c.blkLen >> 6) + 2;
-  const bool raw = c.blkLen < 7 || cSize + minGain >= c.blkLen || cSize >= kBlockSizeMax || c.seqStreamSize > s.seqOutCap;
-  const u32 bsize = raw ? c.blkLen : cSize;
-  const u32 bh = (c.lastBlock ? 1u : 0u) | ((raw ? 0u : 2u) << 1) | (bsize << 3);
+  bool raw = c.blkLen < 7 || cSize + minGain >= c.blkLen || cSize >= kBlockSizeMax || c.seqStreamSize > s.seqOutCap;
+  // RLE block, the reference's rule (zstd_compress.c:2453-2464): never the first block of a frame, only a block whose
+  // sequence store says "maybe" (fewer than 4 sequences and fewer than 10 literals), and then every byte must be equal
+  bool rleBlock = false;
+  if (c.blkPos != 0 && c.nbSeq < 4 && c.litSize < 10 && c.blkLen > 0) {
+    const u8 first = in[c.blkPos];
+    bool same = true;
+    for (u32 k = lane; k < c.blkLen; k += 32) same &= in[c.blkPos + k] == first;
+    rleBlock = __all_sync(0xFFFFFFFFu, same);
+  }
+  if (rleBlock) raw = false;
+  const u32 bsize = (raw || rleBlock) ? c.blkLen : cSize;
+  const u32 bh = (c.lastBlock ? 1u : 0u) | ((rleBlock ? 1u : (raw ? 0u : 2u)) << 1) | (bsize << 3);
   ZRA_PUT(bh); ZRA_PUT(bh >> 8); ZRA_PUT(bh >> 16);
-  if (raw) {
+  if (rleBlock) {
+    ZRA_PUT(in[c.blkPos]);
+  } else if (raw) {
     warp_move(out + op, in + c.blkPos, c.blkLen, lane);
     op += c.blkLen;
   } else {
@@ -923,7 +935,9 @@ __global__ void __launch_bounds__(256) k_enc_assemble_warp(EncJob j, EncView v) 
   if (lane == 0) {
     gc.outPos = op;
     gc.litMode = litMode;
-    if (raw) { gc.rep[0] = c.repSave[0]; gc.rep[1] = c.repSave[1]; gc.rep[2] = c.repSave[2]; }
+    // a raw or RLE block carries no sequences: the decoder's repeat offsets stay what they were (the reference confirms
+    // the block's repcodes only when cSize > 1, zstd_compress.c:2474-2477)
+    if (raw || rleBlock) { gc.rep[0] = c.repSave[0]; gc.rep[1] = c.repSave[1]; gc.rep[2] = c.repSave[2]; }
   }
 }
 
