@@ -1,5 +1,5 @@
 """Archive size of the GPU encoder against the reference's on zstd's own synthetic generator (oracle/_ref/datagen -P<n>),
-text and mixed data: one JSON line per (data, frame size, level). usage: ratio_check.py [mib]"""
+text and mixed data: one JSON line per (data, frame size, level). usage: ratio_check.py [mib] [frame sizes, comma separated]"""
 import json
 import os
 import subprocess
@@ -24,7 +24,7 @@ for p in (20, 50, 80):
 sets["text"] = synth.text(n, seed=3)
 sets["mixed"] = synth.mixed(n, period=65536, seed=3)
 for name, data in sets.items():
-    for fs in (16384, 65536):
+    for fs in ((16384, 65536) if len(sys.argv) < 3 else tuple(int(x) for x in sys.argv[2].split(","))):
         for lvl in (1, 2, 3):
             ref = refzra.ref_compress_mt(data, lvl, fs, True).size
             z = zra_b200.CompressBuffer(data, lvl, fs, True)

@@ -43,7 +43,7 @@ struct EncView {
     f.seqOut = s + lay.offSeqOut + (u64)i * lay.seqOutStride;
     f.seqOutCap = lay.seqOutStride;
     f.cells = s + lay.offCells + (u64)i * 1024;
-    f.cnt = lay.ctaMatch ? reinterpret_cast<u32*>(s + lay.offCnt) + (u64)i * 128 : nullptr;
+    f.cnt = (lay.ctaMatch || lay.ctaBig) ? reinterpret_cast<u32*>(s + lay.offCnt) + (u64)i * 128 : nullptr;
     return f;
   }
   __device__ u8* out(u32 i) const { return s + lay.offOut + (u64)i * lay.outStride; }
@@ -363,6 +363,283 @@ __global__ void __launch_bounds__(T) k_enc_match_cta(EncJob j, EncView v) {
     gc.blkLen = len;
     gc.lastBlock = 1;
     gc.repSave[0] = 1; gc.repSave[1] = 4; gc.repSave[2] = 8;
+    gc.rep[0] = sFinal[2]; gc.rep[1] = sFinal[3]; gc.rep[2] = sFinal[4];
+    gc.nbSeq = nseq;
+    gc.litSize = litPos + rest;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// The same frame-cooperative matcher for frames ABOVE 64 KiB (one launch per 128 KiB block of every frame, `round`).
+// Positions are frame-relative 32-bit numbers, the tables hold 32-bit entries and live in shared memory for the
+// duration of a block: they are loaded from / saved to the frame's HBM table slots between blocks (a block can match into
+// every earlier block of its frame — the window is the frame), and start empty at block 0. Match info per position is
+// offset (24 bits) | length << 24 (7 bits) | "more" (bit 31): frames up to 16 MiB (larger ones keep the thread-per-frame
+// matcher). The literal gather needs no per-sequence side array: sequence chunks are scanned block-wide for their literal
+// and input offsets. Everything else — hashes, lowest-position-wins inserts, verification, the parallel "take" search,
+// the warp-0 greedy walk with the one-byte lazy step and the warp-wide extension — is k_enc_match_cta's.
+// Replaces the thread-per-frame k_enc_match + k_enc_literals for these frames (1.9 GB/s at 256 KiB frames, profiles/r03t).
+constexpr u32 kBigMaxFrame = 1u << 24;
+
+__device__ __forceinline__ void table_insert_min32(u32* cell, u32 pos, u32 roundBase) {
+  u32 cur = *cell;
+  while (cur - roundBase > pos - roundBase) {
+    const u32 prev = atomicCAS(cell, cur, pos);
+    if (prev == cur) break;
+    cur = prev;
+  }
+}
+
+template <int T>
+__global__ void __launch_bounds__(T) k_enc_match_cta_big(EncJob j, EncView v, u32 round) {
+  extern __shared__ __align__(16) u8 smem[];
+  __shared__ u32 sAnchor;
+  __shared__ u32 sFinal[8];
+  __shared__ u32 sHas[T / 32];
+  __shared__ u32 sScanL[T], sScanO[T];
+  const u32 i = blockIdx.x;
+  const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  EncCtx& gc = v.ctx(i);
+  const u32 flen = gc.srcLen;
+  const u32 bstart = round * kBlockSizeMax;
+  const bool activeBlk = bstart < flen || round == 0;
+  if (!activeBlk) {
+    if (tid == 0) gc.blkActive = 0;
+    return;
+  }
+  const u32 blen = flen - bstart < kBlockSizeMax ? flen - bstart : kBlockSizeMax;
+  const u32 bend = bstart + blen;
+  const u32 logS = v.lay.matchLogS, logL = v.lay.matchLogL, mls = v.lay.matchMls;
+  const bool dfast = logL != 0;
+  const u32 nS = 1u << logS, nL = dfast ? (1u << logL) : 0u;
+  u32* tabS = reinterpret_cast<u32*>(smem);
+  u32* tabL = tabS + nS;
+  u32* info = tabL + nL;
+  u32* hist = info + T;   // 256 literal counts, then 36 + 32 + 53 code counts
+  u32* cnt = hist + 256;
+  u16* take = reinterpret_cast<u16*>(cnt + 128);
+  const u8* base = j.in;
+  const u64 fbase = j.inOff + (u64)i * j.frameSize;
+  const EncScratch s = v.frame(i);
+  // ---- tables: empty at block 0, else what the previous block of this frame left
+  {
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    const u32 nSv = nS >> 2, nLv = nL >> 2;
+    if (round == 0) {
+      for (u32 k = tid; k < nSv + nLv; k += T) z[k] = make_uint4(0, 0, 0, 0);
+    } else {
+      const uint4* gS = reinterpret_cast<const uint4*>(s.tabS);
+      const uint4* gL = reinterpret_cast<const uint4*>(s.tabL);
+      for (u32 k = tid; k < nSv; k += T) z[k] = gS[k];
+      for (u32 k = tid; k < nLv; k += T) z[nSv + k] = gL[k];
+    }
+    for (u32 k = tid; k < 256 + 128; k += T) hist[k] = 0;
+    if (tid == 0) sAnchor = bstart;
+  }
+  __syncthreads();
+  EncCtx rc;
+  rc.rep[0] = gc.rep[0]; rc.rep[1] = gc.rep[1]; rc.rep[2] = gc.rep[2];
+  const u32 rep0In = rc.rep[0], rep1In = rc.rep[1], rep2In = rc.rep[2];
+  u32 anchor = bstart, nseq = 0, litPos = 0;
+  const u32 hashEnd = blen >= 16 ? bend - 8 : bstart;  // positions below this can start a match
+  for (u32 rb = bstart; rb < hashEnd; rb += T) {
+    const u32 pos = rb + tid;
+    const u32 curAnchor = sAnchor;
+    if (curAnchor >= rb + T) continue;  // the whole round lies inside a match already taken (uniform)
+    const bool live = pos < hashEnd;
+    u64 x = 0;
+    u32 hS = 0, hL = 0, cS = 0, cL = 0;
+    if (live) {
+      x = gld8(base, fbase + pos);
+      hS = mls <= 4 ? ((u32)x * 2654435761u) >> (32 - logS) : (u32)(((x << (64 - 8 * mls)) * 0x9E3779B97F4A7C15ull) >> (64 - logS));
+      cS = tabS[hS];
+      if (dfast) {
+        hL = (u32)((x * 0xCF1BBCDCB7A56463ull) >> (64 - logL));
+        cL = tabL[hL];
+      }
+    }
+    __syncthreads();
+    if (live) {
+      table_insert_min32(&tabS[hS], pos, rb);
+      if (dfast) table_insert_min32(&tabL[hL], pos, rb);
+    }
+    __syncthreads();
+    u32 e = 0;
+    if (live && pos >= curAnchor && pos > 0) {
+      u32 c2 = tabS[hS];
+      if (c2 < pos && c2 >= rb) cS = c2;
+      bool okS = cS < pos, okL = false;
+      if (dfast) {
+        c2 = tabL[hL];
+        if (c2 < pos && c2 >= rb) cL = c2;
+        okL = cL < pos;
+      }
+      u32 bestLen = 0, bestOff = 0;
+      u32 nL8 = 0, nS8 = 0;
+      if (okL) nL8 = common8(gld8(base, fbase + cL) ^ x);
+      if (okS && (!okL || cS != cL)) nS8 = common8(gld8(base, fbase + cS) ^ x);
+      if (nL8 >= 4 && nL8 >= nS8) { bestLen = nL8; bestOff = pos - cL; }
+      else if (nS8 >= 4) { bestLen = nS8; bestOff = pos - cS; }
+      bool more = false;
+      if (bestLen == 8) {
+        const u32 cand = pos - bestOff;
+        more = true;
+        while (bestLen < kLaneLenCap && pos + bestLen + 8 <= bend) {
+          const u32 c = common8(gld8(base, fbase + pos + bestLen) ^ gld8(base, fbase + cand + bestLen));
+          bestLen += c;
+          if (c < 8) { more = false; break; }
+        }
+      }
+      if (bestLen >= 4 && bestOff < kBigMaxFrame) e = bestOff | (bestLen << 24) | (more ? kInfoMore : 0u);
+    }
+    info[tid] = e;
+    {
+      const u32 bal = __ballot_sync(kFullMask, e != 0);
+      if (lane == 0) sHas[warp] = bal;
+    }
+    __syncthreads();
+    {
+      u32 g = warp;
+      u32 w = sHas[g] & (0xFFFFFFFFu << lane);
+      while (!w && ++g < T / 32) w = sHas[g];
+      u32 q = 0xFFFFu;
+      if (w) {
+        q = g * 32 + ((u32)__ffs((int)w) - 1);
+        if ((q & 31u) != 31u && ((sHas[q >> 5] >> ((q & 31u) + 1u)) & 1u)) {
+          const u32 l1 = (info[q] >> 24) & 0x7Fu, l2 = (info[q + 1] >> 24) & 0x7Fu;
+          if (l1 < 8 && l2 >= 8) q++;
+        }
+      }
+      take[tid] = (u16)q;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      for (;;) {
+        const u32 arrive = anchor > rb ? anchor - rb : 0;
+        if (arrive >= T) break;
+        const u32 k = take[arrive];
+        if (k == 0xFFFFu) break;
+        const u32 ee = info[k];
+        const u32 mpos = rb + k;
+        u32 ml = (ee >> 24) & 0x7Fu;
+        const u32 off = ee & 0xFFFFFFu;
+        if (ee & kInfoMore) {
+          for (;;) {
+            const u32 a = mpos + ml + 4 * lane;
+            u32 diff = 0;
+            if (a + 4 <= bend) {
+              diff = gld4(base, fbase + a) ^ gld4(base, fbase + a - off);
+            } else {
+              for (u32 b = 0; b < 4; b++) {
+                if (a + b >= bend || base[fbase + a + b] != base[fbase + a + b - off]) { diff = 0xFFu << (8 * b); break; }
+              }
+            }
+            const u32 bad = __ballot_sync(kFullMask, diff != 0);
+            if (!bad) { ml += 128; continue; }
+            const u32 first = (u32)__ffs((int)bad) - 1;
+            const u32 d = __shfl_sync(kFullMask, diff, first);
+            ml += 4 * first + (((u32)__ffs((int)d) - 1) >> 3);
+            break;
+          }
+        }
+        const u32 ll = mpos - anchor;
+        const u64 rec = emit_sequence(rc, ll, ml, off);
+        if (lane == 0) s.seqs[nseq] = rec;
+        nseq++;
+        litPos += ll;
+        anchor = mpos + ml;
+      }
+      if (lane == 0) sAnchor = anchor;
+    }
+    __syncthreads();
+  }
+  // ---- save the tables for the frame's next block
+  if (bend < flen) {
+    const uint4* z = reinterpret_cast<const uint4*>(smem);
+    uint4* gS = reinterpret_cast<uint4*>(s.tabS);
+    uint4* gL = reinterpret_cast<uint4*>(s.tabL);
+    const u32 nSv = nS >> 2, nLv = nL >> 2;
+    for (u32 k = tid; k < nSv; k += T) gS[k] = z[k];
+    for (u32 k = tid; k < nLv; k += T) gL[k] = z[nSv + k];
+  }
+  // ---- literal gather + histograms (whole CTA). Every thread takes a contiguous run of sequences; a block-wide scan of
+  // the runs' literal / input byte counts gives each its starting offsets.
+  if (tid == 0) {
+    sFinal[0] = litPos; sFinal[1] = nseq; sFinal[2] = rc.rep[0]; sFinal[3] = rc.rep[1]; sFinal[4] = rc.rep[2];
+    __threadfence_block();
+  }
+  __syncthreads();
+  anchor = sAnchor;
+  litPos = sFinal[0];
+  nseq = sFinal[1];
+  __threadfence();  // the records were written by warp 0 through global memory
+  const u32 per = (nseq + T - 1) / T;
+  const u32 q0 = tid * per < nseq ? tid * per : nseq, q1 = q0 + per < nseq ? q0 + per : nseq;
+  {
+    u32 sumL = 0, sumO = 0;
+    for (u32 q = q0; q < q1; q++) {
+      const u64 rec = s.seqs[q];
+      sumL += seq_ll(rec);
+      sumO += seq_ll(rec) + seq_ml(rec);
+    }
+    sScanL[tid] = sumL;
+    sScanO[tid] = sumO;
+  }
+  __syncthreads();
+  if (warp == 0) {  // exclusive scan of T values by one warp, T / 32 values per lane
+    u32 accL = 0, accO = 0;
+    u32 locL[T / 32], locO[T / 32];
+#pragma unroll
+    for (u32 k = 0; k < T / 32; k++) {
+      locL[k] = accL; locO[k] = accO;
+      accL += sScanL[lane * (T / 32) + k];
+      accO += sScanO[lane * (T / 32) + k];
+    }
+    u32 inL = accL, inO = accO;
+    for (u32 d = 1; d < 32; d <<= 1) {
+      const u32 a = __shfl_up_sync(kFullMask, inL, d), b = __shfl_up_sync(kFullMask, inO, d);
+      if (lane >= d) { inL += a; inO += b; }
+    }
+    const u32 exL = inL - accL, exO = inO - accO;
+#pragma unroll
+    for (u32 k = 0; k < T / 32; k++) {
+      sScanL[lane * (T / 32) + k] = exL + locL[k];
+      sScanO[lane * (T / 32) + k] = exO + locO[k];
+    }
+  }
+  __syncthreads();
+  {
+    u32 to = sScanL[tid], from = bstart + sScanO[tid];
+    for (u32 q = q0; q < q1; q++) {
+      const u64 rec = s.seqs[q];
+      const u32 ll = seq_ll(rec);
+      for (u32 k = 0; k < ll; k++) {
+        const u8 b = base[fbase + from + k];
+        s.lit[to + k] = b;
+        atomicAdd(&hist[b], 1u);
+      }
+      atomicAdd(&cnt[ll_code_fast(ll)], 1u);
+      atomicAdd(&cnt[36 + highbit32(seq_off(rec))], 1u);
+      atomicAdd(&cnt[68 + ml_code_fast(seq_ml(rec) - 3)], 1u);
+      to += ll;
+      from += ll + seq_ml(rec);
+    }
+  }
+  const u32 rest = bend - anchor;
+  for (u32 q = tid; q < rest; q += T) {
+    const u8 b = base[fbase + anchor + q];
+    s.lit[litPos + q] = b;
+    atomicAdd(&hist[b], 1u);
+  }
+  __syncthreads();
+  for (u32 k = tid; k < 256; k += T) s.hist[k] = hist[k];
+  for (u32 k = tid; k < 128; k += T) s.cnt[k] = cnt[k];
+  if (tid == 0) {
+    gc.blkActive = 1;
+    gc.blkPos = bstart;
+    gc.blkLen = blen;
+    gc.lastBlock = bend >= flen;
+    gc.repSave[0] = rep0In; gc.repSave[1] = rep1In; gc.repSave[2] = rep2In;
     gc.rep[0] = sFinal[2]; gc.rep[1] = sFinal[3]; gc.rep[2] = sFinal[4];
     gc.nbSeq = nseq;
     gc.litSize = litPos + rest;
@@ -1047,6 +1324,28 @@ size_t encode_scratch_bytes(u32 nFrames, u32 frameSize, u32 lastFrameLen, int le
   lay->matchPipe = getenv("ZRA_B200_ENC_PIPE") ? (u32)(atoi(getenv("ZRA_B200_ENC_PIPE")) != 0) : (lay->matchSmem >= 40u * 1024u ? 1u : 0u);
   lay->matchSmem += (lay->matchPipe ? 2u : 1u) * (4u + 2u) * lay->matchThreads + 4u * (256u + 128u);
   lay->ctaMatch = frameSize <= 65536u && lay->matchSmem <= 226u * 1024u && !getenv("ZRA_B200_ENC_SERIAL");
+  // frames above 64 KiB (up to 16 MiB): the same matcher with 32-bit tables kept per frame between its blocks
+  lay->ctaBig = 0;
+  if (!lay->ctaMatch && frameSize > 65536u && frameSize <= (1u << 24) && !getenv("ZRA_B200_ENC_SERIAL")) {
+    auto envu = [](const char* k, u32 d) { const char* e = getenv(k); return e ? (u32)strtoul(e, nullptr, 10) : d; };
+    // table logs: a big frame has more history to keep than a 64 KiB one, and with EVERY position inserted a small
+    // table only remembers the recent past. Measured at 256 KiB frames, 32 MiB of text / mixed data, archive size
+    // against the reference's (gpurun_out/r04c, r04d and the sweep after them): double-fast 13/14 -> +3.3 % (L2 text),
+    // +2.9 % (L3 mixed) at 12.9 GB/s; 13/15 -> +1.1 %, +2.4 % at 8.7 GB/s; fast 2^14 -> +3.6 % (L1 text) at 14.5 GB/s,
+    // 2^15 -> +0.9 % at 9.4 GB/s. The 3 % bound of north_star decides: 13/15 and 2^15 (one CTA per SM).
+    u32 bS = ls, bL = ll;
+    if (bL) { if (bS > 13) bS = 13; if (bL > 15) bL = 15; if (bL < 15 && ll >= 14) bL = 15; } else bS = 15;
+    lay->matchLogS = envu("ZRA_B200_ENC_BIG_LOGS", bS);
+    lay->matchLogL = envu("ZRA_B200_ENC_BIG_LOGL", bL);
+    lay->matchThreads = 512;
+    lay->matchPipe = 0;
+    lay->matchSmem = 4u * ((1u << lay->matchLogS) + (lay->matchLogL ? (1u << lay->matchLogL) : 0u)) + 4u * lay->matchThreads + 4u * (256u + 128u) +
+                     2u * lay->matchThreads;
+    // the HBM slots the tables are parked in between blocks must hold them
+    if (lay->tabSEntries < (1u << lay->matchLogS)) lay->tabSEntries = 1u << lay->matchLogS;
+    if (lay->matchLogL && lay->tabLEntries < (1u << lay->matchLogL)) lay->tabLEntries = 1u << lay->matchLogL;
+    lay->ctaBig = lay->matchSmem <= 200u * 1024u ? 1u : 0u;
+  }
   const u32 blk = frameSize < kBlockSizeMax ? frameSize : kBlockSizeMax;
   lay->seqStride = blk / 3 + 2;
   lay->litStride = (blk + 31u) & ~15u;
@@ -1072,7 +1371,7 @@ size_t encode_scratch_bytes(u32 nFrames, u32 frameSize, u32 lastFrameLen, int le
   lay->offStates = take(2ull * 1280 * n);
   lay->offSeqOut = take((size_t)lay->seqOutStride * n);
   lay->offCells = take(1024ull * n);
-  lay->offCnt = take(lay->ctaMatch ? 512ull * n : 16);
+  lay->offCnt = take((lay->ctaMatch || lay->ctaBig) ? 512ull * n : 16);
   lay->offOut = take((size_t)lay->outStride * n);
   lay->offSizes = take(4ull * n);
   lay->offOffsets = take(8ull * (n + 1));
@@ -1086,7 +1385,9 @@ u32 launch_encode_frames(const void* dIn, u64 inOff, u64 inEnd, u32 frameSize, u
   EncJob j{static_cast<const u8*>(dIn), inOff, inEnd, frameSize, nFrames, level, checksum ? 1u : 0u};
   EncView v{static_cast<u8*>(scratch), lay};
   u8* s = static_cast<u8*>(scratch);
-  if (!lay.ctaMatch) {  // hash tables in HBM start empty for every frame
+  if (lay.ctaBig) {
+    cudaFuncSetAttribute(k_enc_match_cta_big<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.matchSmem);
+  } else if (!lay.ctaMatch) {  // hash tables in HBM start empty for every frame
     cudaMemsetAsync(s + lay.offTabS, 0, 4ull * lay.tabSEntries * nFrames, st);
     cudaMemsetAsync(s + lay.offTabL, 0, 4ull * lay.tabLEntries * nFrames, st);
   } else {
@@ -1107,6 +1408,8 @@ u32 launch_encode_frames(const void* dIn, u64 inOff, u64 inEnd, u32 frameSize, u
         else k_enc_match_cta_pipe<256><<<nFrames, 256, lay.matchSmem, st>>>(j, v);
       } else if (lay.matchThreads == 512) k_enc_match_cta<512><<<nFrames, 512, lay.matchSmem, st>>>(j, v);
       else k_enc_match_cta<256><<<nFrames, 256, lay.matchSmem, st>>>(j, v);
+    } else if (lay.ctaBig) {
+      k_enc_match_cta_big<512><<<nFrames, 512, lay.matchSmem, st>>>(j, v, r);
     } else {
       k_enc_match<<<div_up(nFrames, tpb), tpb, 0, st>>>(j, v, r);
       k_enc_literals<<<div_up(nFrames, tpb), tpb, 0, st>>>(j, v);

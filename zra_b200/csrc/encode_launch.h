@@ -15,6 +15,7 @@ struct EncodeLayout {
   uint32_t rounds;                    // blocks per frame
   uint32_t matchPipe;                          // producer / consumer form of the matcher (experiment)
   uint32_t ctaMatch, matchSmem, matchThreads;  // frame-cooperative matcher (frames <= 64 KiB)
+  uint32_t ctaBig;                             // its 32-bit form for frames above 64 KiB (tables parked in HBM between blocks)
   uint32_t matchLogS, matchLogL, matchMls;     // its table logs (16-bit entries) and short-hash width
 };
 
