@@ -556,7 +556,7 @@ def run_compress(args, torch, dist, ctx, rank, world, peak):
                                                  "(includes stitching the seek table)"}
         out["levels"][f"L{level}"] = res
     if world == 1:
-        # frames above 64 KiB take the thread-per-frame matcher (hash tables in HBM): its own number
+        # frames above 64 KiB take the frame-cooperative matcher with 32-bit tables (k_enc_match_cta_big): its own number
         try:
             fs2 = 262144
             cap2 = zra_b200_cap(size, fs2)
@@ -573,7 +573,7 @@ def run_compress(args, torch, dist, ctx, rank, world, peak):
             torch.cuda.synchronize()
             ms2 = e0.elapsed_time(e1)
             out["frames_256KiB_L3"] = {"value": round(size / (ms2 / 1e3) / 1e9, 3), "unit": "GB/s", "ms_per_step": round(ms2, 3),
-                                       "ratio": round(size / n2, 4), "note": "262144 B frames: thread-per-frame matcher"}
+                                       "ratio": round(size / n2, 4), "note": "262144 B frames: k_enc_match_cta_big (one CTA per frame, 32-bit tables in shared memory)"}
             del d_out2
         except Exception as e:  # noqa: BLE001
             out["frames_256KiB_L3"] = {"value": None, "error": repr(e)}

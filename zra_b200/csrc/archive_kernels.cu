@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(kScanBlock) k_scan_block(const u32* __restrict
 
 // Serial exclusive scan of the block totals by one thread (a few thousand values at most).
 __global__ void k_scan_sums(u64* blockSums, u32 nBlocks, u64 base, u64* total) {
-  u64 run = base;
+  u64 run = base == kScanContinue ? *total : base;
   for (u32 b = 0; b < nBlocks; b++) {
     u64 v = blockSums[b];
     blockSums[b] = run;

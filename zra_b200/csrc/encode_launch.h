@@ -30,6 +30,8 @@ uint32_t launch_encode_frames(const void* dIn, uint64_t inOff, uint64_t inEnd, u
 
 // Exclusive scan of the batch's frame sizes (+ `base`), 40-bit seek-table entries at
 // dTable + 5*firstFrame, frames gathered to dFrames + offset. *dTotal (device u64) = base + batch total.
+// base == kScanContinue: the base is what *dTotal holds when the scan runs (batches queued back to back).
+constexpr uint64_t kScanContinue = ~0ull;
 uint32_t launch_scan_gather(void* scratch, const EncodeLayout& lay, uint32_t nFrames, uint64_t base, uint8_t* dTable,
                             uint64_t firstFrame, uint8_t* dFrames, uint64_t framesCap, uint64_t* dTotal, cudaStream_t st);
 

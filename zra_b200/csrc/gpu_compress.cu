@@ -58,9 +58,10 @@ GpuContext::CompressStatus GpuContext::compress_frames(const void* dIn, size_t n
 
 GpuContext::CompressStatus GpuContext::compress_archive(const void* dIn, size_t n, void* dOut, size_t outCap, int level,
                                                         uint32_t frameSize, bool checksum, const uint8_t* metaHost, size_t metaSize,
-                                                        bool refMetaQuirk, cudaStream_t st) {
+                                                        bool refMetaQuirk, cudaStream_t st, const uint8_t* hostIn, uint8_t* hostOut) {
   CompressStatus r;
   bind();
+  const bool hostIo = hostOut != nullptr && (hostIn != nullptr || n == 0);
   const uint32_t table = table_entries(n, frameSize);
   const uint64_t frames = table - 1;
   const size_t storedMeta = refMetaQuirk ? 0 : metaSize;
@@ -85,17 +86,82 @@ GpuContext::CompressStatus GpuContext::compress_archive(const void* dIn, size_t 
     EncodeLayout one;
     size_t perFrame = encode_scratch_bytes(1, frameSize, lastLen, level, &one);
     uint64_t batch = std::min<uint64_t>(std::max<uint64_t>(1, enc_budget() / perFrame), frames);
-    for (uint64_t f0 = 0; f0 < frames; f0 += batch) {
-      uint32_t nb = (uint32_t)std::min<uint64_t>(batch, frames - f0);
-      EncodeLayout lay;
-      size_t bytes = encode_scratch_bytes(nb, frameSize, lastLen, level, &lay);
-      void* s = ensure(scratch, bytes);
-      if (!s) { r.cudaFailed = true; return r; }
-      launches_ += launch_encode_frames(dIn, f0 * frameSize, n, frameSize, nb, level, checksum, s, lay, st);
-      launches_ += launch_scan_gather(s, lay, nb, total, out + tableOff, f0, out + framesOff, outCap - framesOff, dTotal, st);
-      if (check(cudaMemcpyAsync(&total, dTotal, 8, cudaMemcpyDeviceToHost, st), "size readback") ||
-          check(cudaStreamSynchronize(st), "encode kernels")) { r.cudaFailed = true; return r; }
-      if (framesOff + total > outCap) { r.zra = 6; return r; }
+    if (hostIo) {
+      // host pointers: about four batches (at least 8 MiB each; measured best of 2..32), so that the link and the encoder work side by side
+      static const uint64_t parts = [] { const char* e = getenv("ZRA_B200_ENC_IO_PARTS"); return e ? std::max<uint64_t>(1, strtoull(e, nullptr, 10)) : 4ull; }();
+      const uint64_t minFrames = std::max<uint64_t>(1, (8ull << 20) / frameSize);
+      batch = std::min(batch, std::max(minFrames, (frames + parts - 1) / parts));
+      batch = std::max<uint64_t>(batch, (frames + kMaxChunks - 1) / kMaxChunks);  // one pinned end offset per batch
+      if (!ensure_events((frames + batch - 1) / batch + 1)) { r.cudaFailed = true; return r; }
+    }
+    uint8_t* dInW = static_cast<uint8_t*>(const_cast<void*>(dIn));
+    auto upload = [&](uint64_t f0, size_t idx) -> bool {  // the input of the batch that starts at frame f0, on the upload stream
+      if (f0 >= frames) return true;
+      const uint64_t lo = f0 * frameSize, hi = std::min<uint64_t>(n, (f0 + batch) * (uint64_t)frameSize);
+      return !check(cudaMemcpyAsync(dInW + lo, hostIn + lo, hi - lo, cudaMemcpyHostToDevice, upStream_), "input upload") &&
+             !check(cudaEventRecord(upEvents_[idx], upStream_), "upload event");
+    };
+    if (hostIo) {
+      if (check(cudaEventRecord(forkEvent_, st), "fork event") || check(cudaStreamWaitEvent(upStream_, forkEvent_, 0), "fork wait") ||
+          check(cudaStreamWaitEvent(downStream_, forkEvent_, 0), "fork wait") || !upload(0, 0)) { r.cudaFailed = true; return r; }
+    }
+    if (!hostIo) {
+      for (uint64_t f0 = 0; f0 < frames; f0 += batch) {
+        uint32_t nb = (uint32_t)std::min<uint64_t>(batch, frames - f0);
+        EncodeLayout lay;
+        size_t bytes = encode_scratch_bytes(nb, frameSize, lastLen, level, &lay);
+        void* s = ensure(scratch, bytes);
+        if (!s) { r.cudaFailed = true; return r; }
+        launches_ += launch_encode_frames(dIn, f0 * frameSize, n, frameSize, nb, level, checksum, s, lay, st);
+        launches_ += launch_scan_gather(s, lay, nb, kScanContinue, out + tableOff, f0, out + framesOff, outCap - framesOff, dTotal, st);
+        if (check(cudaMemcpyAsync(&total, dTotal, 8, cudaMemcpyDeviceToHost, st), "size readback") ||
+            check(cudaStreamSynchronize(st), "encode kernels")) { r.cudaFailed = true; return r; }
+        if (framesOff + total > outCap) { r.zra = 6; return r; }
+      }
+    } else {
+      // The kernels of every batch are queued without waiting for the host: the running total stays on the device
+      // (kScanContinue) and each batch leaves its end offset in pinned memory. The host follows one batch behind and
+      // sends batch b's frames down while batch b + 1 is being compressed and batch b + 2 is coming up.
+      uint64_t* ends = reinterpret_cast<uint64_t*>(summaryHost_);
+      auto retire = [&](size_t b) -> bool {  // batch b has finished: download its frames
+        if (check(cudaEventSynchronize(doneEvents_[b]), "encode kernels")) { r.cudaFailed = true; return false; }
+        const uint64_t before = total;
+        total = ends[b];
+        if (framesOff + total > outCap) { r.zra = 6; return false; }
+        if (total > before &&
+            check(cudaMemcpyAsync(hostOut + framesOff + before, out + framesOff + before, total - before, cudaMemcpyDeviceToHost, downStream_),
+                  "archive download")) { r.cudaFailed = true; return false; }
+        return true;
+      };
+      auto drain = [&] { cudaStreamSynchronize(pool_[0]); cudaStreamSynchronize(pool_[1]); cudaStreamSynchronize(upStream_); cudaStreamSynchronize(downStream_); };
+      // two lanes with a scratch area each: the thread-per-frame stages of a batch (planning, table building) are
+      // latency bound and take the same time for 1 000 frames as for 16 000, so they run beside the next batch's matcher
+      cudaStream_t lanes[2] = {pool_[0], pool_[1]};
+      EncodeLayout layMax;
+      const size_t laneBytes = (encode_scratch_bytes((uint32_t)batch, frameSize, lastLen, level, &layMax) + 255) & ~size_t(255);
+      uint8_t* s0 = static_cast<uint8_t*>(ensure(scratch, 2 * laneBytes));
+      if (!s0) { r.cudaFailed = true; return r; }
+      if (check(cudaStreamWaitEvent(lanes[0], forkEvent_, 0), "fork wait") || check(cudaStreamWaitEvent(lanes[1], forkEvent_, 0), "fork wait")) {
+        r.cudaFailed = true;
+        return r;
+      }
+      size_t bi = 0;
+      for (uint64_t f0 = 0; f0 < frames; f0 += batch, bi++) {
+        uint32_t nb = (uint32_t)std::min<uint64_t>(batch, frames - f0);
+        cudaStream_t ln = lanes[bi & 1];
+        void* s = s0 + (bi & 1) * laneBytes;
+        EncodeLayout lay;
+        encode_scratch_bytes(nb, frameSize, lastLen, level, &lay);
+        if (!upload(f0 + batch, bi + 1) || check(cudaStreamWaitEvent(ln, upEvents_[bi], 0), "upload wait")) { drain(); r.cudaFailed = true; return r; }
+        launches_ += launch_encode_frames(dIn, f0 * frameSize, n, frameSize, nb, level, checksum, s, lay, ln);
+        // the running total is handed from batch to batch
+        if (bi > 0 && check(cudaStreamWaitEvent(ln, doneEvents_[bi - 1], 0), "batch order")) { drain(); r.cudaFailed = true; return r; }
+        launches_ += launch_scan_gather(s, lay, nb, kScanContinue, out + tableOff, f0, out + framesOff, outCap - framesOff, dTotal, ln);
+        if (check(cudaMemcpyAsync(&ends[bi], dTotal, 8, cudaMemcpyDeviceToHost, ln), "size readback") ||
+            check(cudaEventRecord(doneEvents_[bi], ln), "batch event")) { drain(); r.cudaFailed = true; return r; }
+        if (bi > 0 && !retire(bi - 1)) { drain(); return r; }
+      }
+      if (!retire(bi - 1)) { drain(); return r; }
     }
   } else {
     // no frames: the table is the single zero sentinel
@@ -118,6 +184,13 @@ GpuContext::CompressStatus GpuContext::compress_archive(const void* dIn, size_t 
   if (check(cudaMemcpyAsync(out + 14, h, 4, cudaMemcpyHostToDevice, st), "hash upload") ||
       check(cudaStreamSynchronize(st), "hash upload")) { r.cudaFailed = true; return r; }
   r.total = framesOff + total;
+  if (hostIo) {  // header, metadata, seek table; then every download must have landed
+    if (check(cudaMemcpyAsync(hostOut, out, std::min<size_t>(framesOff, r.total), cudaMemcpyDeviceToHost, st), "header download") ||
+        check(cudaStreamSynchronize(st), "header download") || check(cudaStreamSynchronize(downStream_), "archive download")) {
+      r.cudaFailed = true;
+      return r;
+    }
+  }
   return r;
 }
 

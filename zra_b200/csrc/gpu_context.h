@@ -108,8 +108,11 @@ class GpuContext {
   // dIn[0..n) -> complete archive at dOut (header, metadata, 40-bit seek table, frames), all on the device.
   // refMetaQuirk reproduces zra::CompressBuffer's layout for a non-empty meta: the
   // header records metaSize but no metadata bytes are stored.
+  // hostIn / hostOut (both or neither): the input lives in HOST memory and the archive is wanted there. The frames are
+  // then compressed in batches whose upload (batch b + 1), kernels (batch b) and download (batch b - 1) overlap.
   CompressStatus compress_archive(const void* dIn, size_t n, void* dOut, size_t outCap, int level, uint32_t frameSize,
-                                  bool checksum, const uint8_t* metaHost, size_t metaSize, bool refMetaQuirk, cudaStream_t st);
+                                  bool checksum, const uint8_t* metaHost, size_t metaSize, bool refMetaQuirk, cudaStream_t st,
+                                  const uint8_t* hostIn = nullptr, uint8_t* hostOut = nullptr);
   // dIn[0..n) -> zstd frames back to back at dOut (no header); sizesHost[i] = compressed size of frame i.
   CompressStatus compress_frames(const void* dIn, size_t n, uint32_t frameSize, int level, bool checksum, void* dOut,
                                  size_t outCap, uint64_t* sizesHost, cudaStream_t st);

@@ -131,16 +131,13 @@ OpStatus host_compress_buffer(GpuContext* g, const uint8_t* in, size_t n, uint8_
   uint8_t* dIn = static_cast<uint8_t*>(g->ensure(g->stageIn, pad4(n) + 64));
   uint8_t* dOut = static_cast<uint8_t*>(g->ensure(g->stageOut, outCap + 64));
   if (!dIn || !dOut) return cuda_failed();
-  if (n && g->check(cudaMemcpyAsync(dIn, in, n, cudaMemcpyHostToDevice, st), "input upload")) return cuda_failed();
   // zero the slack the 32-bit readers may touch past the end of the input
   if (g->check(cudaMemsetAsync(dIn + n, 0, pad4(n) + 64 - n, st), "memset")) return cuda_failed();
+  // the input goes up, the frames are compressed and the archive comes down in overlapping batches (gpu_compress.cu)
   GpuContext::CompressStatus r = g->compress_archive(dIn, n, dOut, outCap, level, frameSize, checksum, meta, metaSize,
-                                                     /*refMetaQuirk=*/true, st);
+                                                     /*refMetaQuirk=*/true, st, in, out);
   if (r.cudaFailed) return cuda_failed();
   if (r.zra) return zra_error(r.zra);
-  if (g->check(cudaMemcpyAsync(out, dOut, r.total, cudaMemcpyDeviceToHost, st), "archive download") ||
-      g->check(cudaStreamSynchronize(st), "archive download"))
-    return cuda_failed();
   *written = r.total;
   return OpStatus{};
 }
