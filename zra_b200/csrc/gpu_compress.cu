@@ -58,10 +58,11 @@ GpuContext::CompressStatus GpuContext::compress_frames(const void* dIn, size_t n
 
 GpuContext::CompressStatus GpuContext::compress_archive(const void* dIn, size_t n, void* dOut, size_t outCap, int level,
                                                         uint32_t frameSize, bool checksum, const uint8_t* metaHost, size_t metaSize,
-                                                        bool refMetaQuirk, cudaStream_t st, const uint8_t* hostIn, uint8_t* hostOut) {
+                                                        bool refMetaQuirk, cudaStream_t st, const uint8_t* hostIn, uint8_t* hostOut,
+                                                        uint8_t* hostFrames) {
   CompressStatus r;
   bind();
-  const bool hostIo = hostOut != nullptr && (hostIn != nullptr || n == 0);
+  const bool hostIo = (hostOut != nullptr || hostFrames != nullptr) && (hostIn != nullptr || n == 0);
   const uint32_t table = table_entries(n, frameSize);
   const uint64_t frames = table - 1;
   const size_t storedMeta = refMetaQuirk ? 0 : metaSize;
@@ -69,6 +70,7 @@ GpuContext::CompressStatus GpuContext::compress_archive(const void* dIn, size_t 
   const size_t framesOff = tableOff + kEntrySize * (size_t)table;
   if (outCap < framesOff) { r.zra = 6; return r; }
   uint8_t* out = static_cast<uint8_t*>(dOut);
+  if (hostIo && !hostFrames) hostFrames = hostOut + framesOff;
   uint8_t fixed[kFixedHeaderSize];
   write_fixed_header(fixed, n, table, frameSize, (uint32_t)metaSize);
   if (check(cudaMemcpyAsync(out, fixed, sizeof(fixed), cudaMemcpyHostToDevice, st), "header upload")) { r.cudaFailed = true; return r; }
@@ -87,9 +89,12 @@ GpuContext::CompressStatus GpuContext::compress_archive(const void* dIn, size_t 
     size_t perFrame = encode_scratch_bytes(1, frameSize, lastLen, level, &one);
     uint64_t batch = std::min<uint64_t>(std::max<uint64_t>(1, enc_budget() / perFrame), frames);
     if (hostIo) {
-      // host pointers: about four batches (at least 8 MiB each; measured best of 2..32), so that the link and the encoder work side by side
+      // host pointers: about four batches (measured best of 2..32), at least 32 MiB each (a batch's thread-per-frame
+      // stages cost the same 2-3 ms for 256 frames as for 4 096: 64 MiB calls of the streaming Compressor run 7.2 GB/s
+      // with 16 MiB batches, 10.9 with 32 MiB), so that the link and the encoder work side by side
       static const uint64_t parts = [] { const char* e = getenv("ZRA_B200_ENC_IO_PARTS"); return e ? std::max<uint64_t>(1, strtoull(e, nullptr, 10)) : 4ull; }();
-      const uint64_t minFrames = std::max<uint64_t>(1, (8ull << 20) / frameSize);
+      static const uint64_t minMb = [] { const char* e = getenv("ZRA_B200_ENC_IO_MIN_MB"); return e ? std::max<uint64_t>(1, strtoull(e, nullptr, 10)) : 32ull; }();
+      const uint64_t minFrames = std::max<uint64_t>(1, (minMb << 20) / frameSize);
       batch = std::min(batch, std::max(minFrames, (frames + parts - 1) / parts));
       batch = std::max<uint64_t>(batch, (frames + kMaxChunks - 1) / kMaxChunks);  // one pinned end offset per batch
       if (!ensure_events((frames + batch - 1) / batch + 1)) { r.cudaFailed = true; return r; }
@@ -129,7 +134,7 @@ GpuContext::CompressStatus GpuContext::compress_archive(const void* dIn, size_t 
         total = ends[b];
         if (framesOff + total > outCap) { r.zra = 6; return false; }
         if (total > before &&
-            check(cudaMemcpyAsync(hostOut + framesOff + before, out + framesOff + before, total - before, cudaMemcpyDeviceToHost, downStream_),
+            check(cudaMemcpyAsync(hostFrames + before, out + framesOff + before, total - before, cudaMemcpyDeviceToHost, downStream_),
                   "archive download")) { r.cudaFailed = true; return false; }
         return true;
       };
@@ -185,8 +190,9 @@ GpuContext::CompressStatus GpuContext::compress_archive(const void* dIn, size_t 
       check(cudaStreamSynchronize(st), "hash upload")) { r.cudaFailed = true; return r; }
   r.total = framesOff + total;
   if (hostIo) {  // header, metadata, seek table; then every download must have landed
-    if (check(cudaMemcpyAsync(hostOut, out, std::min<size_t>(framesOff, r.total), cudaMemcpyDeviceToHost, st), "header download") ||
-        check(cudaStreamSynchronize(st), "header download") || check(cudaStreamSynchronize(downStream_), "archive download")) {
+    if ((hostOut && (check(cudaMemcpyAsync(hostOut, out, std::min<size_t>(framesOff, r.total), cudaMemcpyDeviceToHost, st), "header download") ||
+                     check(cudaStreamSynchronize(st), "header download"))) ||
+        check(cudaStreamSynchronize(downStream_), "archive download")) {
       r.cudaFailed = true;
       return r;
     }

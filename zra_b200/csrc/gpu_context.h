@@ -110,9 +110,11 @@ class GpuContext {
   // header records metaSize but no metadata bytes are stored.
   // hostIn / hostOut (both or neither): the input lives in HOST memory and the archive is wanted there. The frames are
   // then compressed in batches whose upload (batch b + 1), kernels (batch b) and download (batch b - 1) overlap.
+  // hostFrames (optional): the frames go there instead of behind the header at hostOut (hostOut may then be null: the
+  // header and the seek table stay on the device, at dOut).
   CompressStatus compress_archive(const void* dIn, size_t n, void* dOut, size_t outCap, int level, uint32_t frameSize,
                                   bool checksum, const uint8_t* metaHost, size_t metaSize, bool refMetaQuirk, cudaStream_t st,
-                                  const uint8_t* hostIn = nullptr, uint8_t* hostOut = nullptr);
+                                  const uint8_t* hostIn = nullptr, uint8_t* hostOut = nullptr, uint8_t* hostFrames = nullptr);
   // dIn[0..n) -> zstd frames back to back at dOut (no header); sizesHost[i] = compressed size of frame i.
   CompressStatus compress_frames(const void* dIn, size_t n, uint32_t frameSize, int level, bool checksum, void* dOut,
                                  size_t outCap, uint64_t* sizesHost, cudaStream_t st);

@@ -144,19 +144,33 @@ OpStatus host_compress_buffer(GpuContext* g, const uint8_t* in, size_t n, uint8_
 
 OpStatus host_compress_frames(GpuContext* g, const uint8_t* in, size_t n, uint32_t frameSize, int level, bool checksum, uint8_t* out,
                               size_t outCap, uint64_t* sizes, size_t* produced) {
+  *produced = 0;
+  if (!n) return OpStatus{};
+  // The frames of one call are a complete archive without metadata: the archive path (upload, kernels and download
+  // overlapped in batches) builds it in device memory, the frames go straight to `out`, and the seek table that stays
+  // on the device gives the frame sizes.
   cudaStream_t st = g->stream();
+  const uint64_t frames = (n + frameSize - 1) / frameSize;
+  const size_t tableOff = kFixedHeaderSize, framesOff = tableOff + kEntrySize * (size_t)(frames + 1);
   uint8_t* dIn = static_cast<uint8_t*>(g->ensure(g->stageIn, pad4(n) + 64));
-  uint8_t* dOut = static_cast<uint8_t*>(g->ensure(g->stageOut, outCap + 64));
+  uint8_t* dOut = static_cast<uint8_t*>(g->ensure(g->stageOut, framesOff + outCap + 64));
   if (!dIn || !dOut) return cuda_failed();
-  if (n && g->check(cudaMemcpyAsync(dIn, in, n, cudaMemcpyHostToDevice, st), "input upload")) return cuda_failed();
   if (g->check(cudaMemsetAsync(dIn + n, 0, pad4(n) + 64 - n, st), "memset")) return cuda_failed();
-  GpuContext::CompressStatus r = g->compress_frames(dIn, n, frameSize, level, checksum, dOut, outCap, sizes, st);
+  GpuContext::CompressStatus r = g->compress_archive(dIn, n, dOut, framesOff + outCap, level, frameSize, checksum, nullptr, 0, false, st, in,
+                                                     nullptr, out);
   if (r.cudaFailed) return cuda_failed();
   if (r.zra) return zra_error(r.zra);
-  if (r.total && (g->check(cudaMemcpyAsync(out, dOut, r.total, cudaMemcpyDeviceToHost, st), "frames download") ||
-                  g->check(cudaStreamSynchronize(st), "frames download")))
+  std::vector<uint8_t> table(kEntrySize * (size_t)(frames + 1));
+  if (g->check(cudaMemcpyAsync(table.data(), dOut + tableOff, table.size(), cudaMemcpyDeviceToHost, st), "table download") ||
+      g->check(cudaStreamSynchronize(st), "table download"))
     return cuda_failed();
-  *produced = r.total;
+  uint64_t prev = get_le(table.data(), 5);
+  for (uint64_t f = 0; f < frames; f++) {
+    const uint64_t next = get_le(table.data() + kEntrySize * (size_t)(f + 1), 5);
+    sizes[f] = next - prev;
+    prev = next;
+  }
+  *produced = r.total - framesOff;
   return OpStatus{};
 }
 
