@@ -154,6 +154,47 @@ def test_streaming_compressor_matches_buffer_api_and_handles_metadata():
     assert np.array_equal(np.concatenate(parts), one[parse_header(one)["size"]:])
 
 
+def test_host_compress_in_overlapped_batches_small_batches_forced():
+    """The host-pointer compress path works in batches whose upload, kernels and download overlap (two lanes, running
+    total on the device). The batch floor is 32 MiB, so ordinary test sizes are one batch: a child process lowers the
+    floor to 1 MiB (the setting is read once per process) and runs the one-shot and the streaming API over ragged,
+    multi-batch inputs; the archives must be byte-identical to single-batch ones and decode through the oracle."""
+    import os
+    import subprocess
+    import sys
+
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, "tests")
+import zra_b200, refzra
+from zra_b200 import synth
+from common import parse_header
+for n, fs, lvl in [((9 << 20) + 4321, 65536, 3), ((5 << 20) + 17, 16384, 1), ((6 << 20), 262144, 3), (70000, 65536, 3)]:
+    data = synth.mixed(n, period=fs, seed=3, threads=4)
+    z = zra_b200.CompressBuffer(data, lvl, fs, True)
+    assert np.array_equal(refzra.oracle_decompress_buffer(z), data), ("one-shot", n, fs)
+    c = zra_b200.Compressor(n, lvl, fs, True)
+    cut = (n // fs // 2) * fs
+    parts = [c.Compress(data[:cut]), c.Compress(data[cut:])] if cut else [c.Compress(data)]
+    assert np.array_equal(np.concatenate([c.GetHeader()] + parts), z), ("streaming", n, fs)
+    np.save(sys.argv[1] + f"_{n}_{fs}.npy", z)
+print("ok")
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    import tempfile
+
+    with tempfile.TemporaryDirectory() as tmp:
+        outs = {}
+        for tag, env in (("multi", {"ZRA_B200_ENC_IO_MIN_MB": "1", "ZRA_B200_ENC_IO_PARTS": "5"}), ("single", {"ZRA_B200_ENC_IO_PARTS": "1"})):
+            r = subprocess.run([sys.executable, "-c", code, os.path.join(tmp, tag)], cwd=root, env={**os.environ, **env},
+                               capture_output=True, text=True, timeout=600)
+            assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+            outs[tag] = sorted(f for f in os.listdir(tmp) if f.startswith(tag))
+        assert len(outs["multi"]) == len(outs["single"]) == 4
+        for a, b in zip(outs["multi"], outs["single"]):
+            assert np.array_equal(np.load(os.path.join(tmp, a)), np.load(os.path.join(tmp, b))), (a, b)
+
+
 def test_device_compress_with_metadata(tmp_path):
     import torch
 
