@@ -132,24 +132,27 @@ ZRA_DEV void cp_async_commit() {
 #endif
 }
 
-// Refill point of the lock-step loops: at most two steps (< 6 words) are consumed between two points.
-// cp.async groups are tracked per WARP, and with 32 unrelated streams some lane asks for a group at almost every point:
-// waiting for "all but the newest group" would expose the memory latency of the previous point's request at every
-// point (profiles/r03e: 19 % of the kernel's stall samples). So a lane keeps its requests 24..28 words below its
-// cursor — one group per point — and the warp waits for all but the newest THREE groups: what a lane requested three or
-// more points ago has landed, i.e. everything above reqW + 12 <= cursor - 6. A stream of maximal sequences (> 4 words a
-// point) could outrun one request per point; then (any lane closer than 18 words) every lane may request a second
-// group and the warp waits for everything.
+// Refill point of the lock-step loops: at most kSeqPointSteps steps (4 x 89 bits: the cursor crosses at most 12 word
+// boundaries, and the window reaches 3 words below it) are consumed between two points, so a point must leave every
+// word from the cursor down to cursor - 15 landed. cp.async groups are tracked per WARP, and with 32 unrelated streams
+// some lane asks for a group at almost every point: a lane keeps its requests 24..28 words below its cursor — one
+// group per point covers the usual consumption of ~3 words — and the warp waits for all but the NEWEST group: what a
+// lane requested at an earlier point has had a whole point (~1300 cycles) to land, i.e. everything above reqW + 4 <=
+// cursor - 20. A stream of long sequences (> 4 words a point) outruns one request per point; then (any lane closer
+// than 20 words after its request) every such lane requests until it is 20 words ahead again and the warp waits for
+// everything. (Two steps per point and "all but the newest three" before: the predicated-off request block was 18 %
+// of the kernel's instructions, profiles/r03w.)
+constexpr u32 kSeqPointSteps = 4;
 ZRA_DEV void refill_point(FastSeq& s, const SeqSm& sm, bool active) {
   const i32 kw = (s.p - 1) >> 5;
   ring_request(s, sm, kw, 24, active);
-  if (__any_sync(kSeqFull, active && s.reqW > 0 && kw - s.reqW < 18)) {
-    ring_request(s, sm, kw, 24, active);
+  if (__any_sync(kSeqFull, active && s.reqW > 0 && kw - s.reqW < 20)) {
+    for (u32 g = 0; g < 3; g++) ring_request(s, sm, kw, 20, active);
     cp_async_commit();
     cp_async_wait<0>();
   } else {
     cp_async_commit();
-    cp_async_wait<3>();
+    cp_async_wait<1>();
   }
 }
 
@@ -343,7 +346,7 @@ __global__ void __launch_bounds__(32) k_seq_decode(const u8* __restrict__ src, c
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-    for (u32 k = 0; k < steps; k += 2) {
+    for (u32 k = 0; k < steps; k += kSeqPointSteps) {
       refill_point(st, sm, active);
       // every lane steps (a lane without a frame walks harmlessly through its own slot and ring): no branch, only the
       // record store is predicated
@@ -353,9 +356,17 @@ __global__ void __launch_bounds__(32) k_seq_decode(const u8* __restrict__ src, c
         const u64 r1 = fast_step<false>(sm, st);
         if (active) out[1] = r1;
       }
-      out += 2;
+      if (k + 2 < steps) {
+        const u64 r2 = fast_step<false>(sm, st);
+        if (active) out[2] = r2;
+      }
+      if (k + 3 < steps) {
+        const u64 r3 = fast_step<false>(sm, st);
+        if (active) out[3] = r3;
+      }
+      out += kSeqPointSteps;
     }
-    if (active && (steps & 1u)) out -= 1;
+    if (active) out -= (kSeqPointSteps - (steps & (kSeqPointSteps - 1u))) & (kSeqPointSteps - 1u);
     // ---- lanes at their last sequence: no state update, then the end-of-block checks
     if (active && st.n - st.i == 1u) {
       ring_request(st, sm, (st.p - 1) >> 5, 24, true);
