@@ -136,23 +136,30 @@ ZRA_DEV void cp_async_commit() {
 // boundaries, and the window reaches 3 words below it) are consumed between two points, so a point must leave every
 // word from the cursor down to cursor - 15 landed. cp.async groups are tracked per WARP, and with 32 unrelated streams
 // some lane asks for a group at almost every point: a lane keeps its requests 24..28 words below its cursor — one
-// group per point covers the usual consumption of ~3 words — and the warp waits for all but the NEWEST group: what a
-// lane requested at an earlier point has had a whole point (~1300 cycles) to land, i.e. everything above reqW + 4 <=
-// cursor - 20. A stream of long sequences (> 4 words a point) outruns one request per point; then (any lane closer
-// than 20 words after its request) every such lane requests until it is 20 words ahead again and the warp waits for
-// everything. (Two steps per point and "all but the newest three" before: the predicated-off request block was 18 %
-// of the kernel's instructions, profiles/r03w.)
+// group per point covers the usual consumption of 1.5 .. 3 words — and the warp waits for all but the newest TWO
+// groups: what a lane requested two points ago has had ~2600 cycles to land (the slowest of 32 DRAM requests is what the
+// warp waits for: with one point of slack the wait was 60 cycles per step, profiles/r05), i.e. everything above
+// reqW + 8 <= cursor - 16. A stream of long sequences (> 5 words a point) outruns one request per point; then (any lane
+// closer than kSeqFloor words after its request) every such lane tops up and the warp waits for everything. (Two steps
+// per point and "all but the newest three" before: the predicated-off request block was 18 % of the kernel's
+// instructions, profiles/r03w.)
 constexpr u32 kSeqPointSteps = 4;
+#ifndef ZRA_SEQ_PENDING
+#define ZRA_SEQ_PENDING 2
+#endif
+constexpr int kSeqPending = ZRA_SEQ_PENDING;               // groups that may still be in flight after a point
+constexpr i32 kSeqLead = 24;                               // a request goes out while the cursor is closer than this to reqW (32-word ring: < 28 keeps every row above the cursor's window intact)
+constexpr i32 kSeqFloor = 15 + 4 * kSeqPending;             // ... which leaves reqW + 4 * kSeqPending landed: the cursor must be this far above reqW
 ZRA_DEV void refill_point(FastSeq& s, const SeqSm& sm, bool active) {
   const i32 kw = (s.p - 1) >> 5;
-  ring_request(s, sm, kw, 24, active);
-  if (__any_sync(kSeqFull, active && s.reqW > 0 && kw - s.reqW < 20)) {
-    for (u32 g = 0; g < 3; g++) ring_request(s, sm, kw, 20, active);
+  ring_request(s, sm, kw, kSeqLead, active);
+  if (__any_sync(kSeqFull, active && s.reqW > 0 && kw - s.reqW < kSeqFloor)) {
+    for (u32 g = 0; g < 3; g++) ring_request(s, sm, kw, kSeqFloor, active);
     cp_async_commit();
     cp_async_wait<0>();
   } else {
     cp_async_commit();
-    cp_async_wait<1>();
+    cp_async_wait<kSeqPending>();
   }
 }
 
