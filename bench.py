@@ -65,10 +65,18 @@ def build_archive(size, frame_size, level, seed):
     data = synth.text(size, seed=seed)
     archive = refzra.ref_compress_mt(data, level, frame_size, True)
     try:
-        data.tofile(tag + ".raw")
-        archive.tofile(tag + ".zra")
+        import shutil
+
+        # (only while /tmp keeps plenty of room: 8 ranks x 8 GiB shards must not fill the disk the JSON line goes to)
+        if shutil.disk_usage("/tmp").free > 4 * (data.size + archive.size) + (8 << 30) and data.size <= (2 << 30):
+            data.tofile(tag + ".raw")
+            archive.tofile(tag + ".zra")
     except OSError:
-        pass
+        for ext in (".raw", ".zra"):
+            try:
+                os.remove(tag + ext)
+            except OSError:
+                pass
     return data, archive
 
 
@@ -853,9 +861,10 @@ def run_gpu(args):
         for _ in range(2):
             dist.all_gather_into_tensor(out_all, d_out)
         sums = torch.zeros(world, dtype=torch.int64, device="cuda")
-        sums[rank] = d_ref.sum(dtype=torch.int64)
+        # (a checksum of 64-bit words: no widened temporary, which at 8 GiB per shard would not fit)
+        sums[rank] = d_ref.view(torch.int64).sum()
         dist.all_reduce(sums)
-        got = out_all.view(world, size).sum(dim=1, dtype=torch.int64)
+        got = out_all.view(torch.int64).view(world, size // 8).sum(dim=1)
         assert torch.equal(got, sums), "gathered archive differs from the shards' originals"
         assert torch.equal(out_all[rank * size:(rank + 1) * size], d_ref)
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -900,7 +909,7 @@ def run_gpu(args):
                 out_all.zero_()
                 overlapped()
                 torch.cuda.synchronize()
-                got = out_all.view(world, size).sum(dim=1, dtype=torch.int64)
+                got = out_all.view(torch.int64).view(world, size // 8).sum(dim=1)
                 assert torch.equal(got, sums), "overlapped gather: the gathered archive differs from the shards' originals"
                 assert torch.equal(mine, d_ref)
                 barrier()
