@@ -365,12 +365,18 @@ def run_ra(args, torch, dist, ctx, rank, world, peak):
     # end to end: offsets from pinned host memory, results back to pinned host memory, every step
     h_off = torch.from_numpy(offs.view(np.int64)).pin_memory()
     h_out = torch.empty(count * rsz, dtype=torch.uint8).pin_memory()
+    # (one batch per step: splitting it so that a sub-batch's reads go down while the next decodes is SLOWER — 5.1 M
+    # against 7.0 M reads/s with four sub-batches — because a batch's decode is latency-bound and takes about as long for
+    # 16 384 reads as for 65 536)
     def e2e_step():
         d_off.copy_(h_off, non_blocking=True)
         step()
         h_out.copy_(d_out, non_blocking=True)
         torch.cuda.synchronize()
+    h_out.zero_()
     e2e_step()
+    assert np.array_equal(h_out.numpy().reshape(count, rsz), data[(offs.astype(np.int64).reshape(-1, 1) + np.arange(rsz).reshape(1, -1))]), \
+        "random-access result (host path) differs from the original"
     t0 = time.perf_counter()
     for _ in range(steps):
         e2e_step()
