@@ -301,15 +301,6 @@ ZRA_DEV void exec_block(const u8* src, u8* dst, const FrameDesc& d, const FrameC
         rowp += 32 * kExecRowBlock; mkp += 32 * kExecRowBlock; tp += 32 * kExecRowBlock; tb += 32 * kExecRowBlock; bit <<= kExecRowBlock;
       }
       __syncwarp();
-#if defined(__CUDA_ARCH__)
-      // the NEXT group's match sources (its records were requested at the top of this iteration and have landed by
-      // now): most are far back in the frame and miss L1 / L2; the prefetch has the rest of this iteration to land
-      // (k_seq_execute 2.55 -> 2.52 ms, the step 4.93 -> 4.80; into L2 only: 4.83 .. 4.86)
-      if (base + 32 < nbSeq) {
-        const u8* pf = blk + (i64)(i32)(rec_out_end(sNext) - rec_off(sNext)) - 1;
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
-      }
-#endif
       // ---- pass two: bytes whose source is in the tile, row by row
       u32 rows = __reduce_or_sync(kExecFull, depRows);
       while (rows) {
